@@ -1,0 +1,153 @@
+/* pislam_b200 -- C ABI of the B200 (sm_100a) ORB front-end.
+ *
+ * This is the whole drop-in boundary: plain pointers and sizes, no C++/torch types.  The
+ * reference (0xfaded/pislam) is a header-only C++ template library without any FFI; the
+ * `pislam::` template wrappers in include/pislam/{Fast,Harris,Orb,Brief,Util}.h forward to the
+ * entry points below with their template arguments (vstep, border, logBucketSize, bucketLimit,
+ * words) as run-time integers.  Every entry point cites the reference function it replaces.
+ *
+ * Conventions
+ *   - status return: 0 = ok; -(cudaError_t) for a CUDA failure; PISLAM_ERR_* otherwise.
+ *     Nothing throws.  There is NO CPU fallback: without a usable GPU pislam_b200_create fails.
+ *   - one pislam_ctx per host thread and GPU; it owns one CUDA stream, device staging buffers
+ *     and scratch.  Calls on one ctx are serialised by the caller (the reference is
+ *     single-threaded and re-entrant; use one ctx per thread for concurrency).
+ *   - images are row-major uint8 with a row pitch of `vstep` bytes; `img` / `out` point at the
+ *     first row of the LEVEL being processed, like the reference's `uint8_t img[][vstep]`.
+ *   - "literal stage" calls take HOST pointers, do H2D + kernel + D2H and leave the host
+ *     buffers exactly as the reference would.  The fused calls accept host OR device pointers
+ *     (detected with cudaPointerGetAttributes) for every buffer.
+ */
+#ifndef PISLAM_B200_H_
+#define PISLAM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PISLAM_OK 0
+#define PISLAM_ERR_INVALID_ARG (-10001) /* null pointer, negative size, words outside 1..8 ... */
+#define PISLAM_ERR_UNSUPPORTED (-10002) /* geometry outside the fused kernels' domain, see DESIGN.md */
+#define PISLAM_ERR_CAPACITY (-10003)    /* more keypoints than `cap`; *n receives the required count */
+#define PISLAM_ERR_NO_DEVICE (-10004)   /* no CUDA device / wrong architecture */
+#define PISLAM_ERR_NCCL (-11000)        /* -11000 - ncclResult_t */
+
+#define PISLAM_MAX_LEVELS 16
+
+typedef struct pislam_ctx pislam_ctx;
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* max_stack_bytes / max_keypoints are sizing hints (buffers grow on demand). */
+int pislam_b200_create(pislam_ctx** ctx, int device, size_t max_stack_bytes, int max_keypoints);
+int pislam_b200_destroy(pislam_ctx* ctx);
+const char* pislam_b200_error_string(int status);
+/* The CUDA stream (cudaStream_t) all work of this ctx is issued on. */
+void* pislam_b200_stream(pislam_ctx* ctx);
+/* Blocks until everything issued on the ctx stream has finished. */
+int pislam_b200_synchronize(pislam_ctx* ctx);
+/* Number of kernel launches issued by this ctx since creation (bench.py's gpu_launches). */
+long pislam_b200_launch_count(pislam_ctx* ctx);
+
+/* ---- literal stages (host buffers) ---------------------------------------------------------- */
+/* pislam::fastDetect<vstep,border>(width,height,img,out,threshold)        reference Fast.h:54-158 */
+int pislam_b200_fast_detect(pislam_ctx* ctx, const uint8_t* img, uint8_t* out, int vstep, int border,
+                            int width, int height, int threshold);
+/* pislam::fastScoreHarris<vstep,border>(width,height,img,threshold,out)   reference Fast.h:166-180 */
+int pislam_b200_fast_score_harris(pislam_ctx* ctx, const uint8_t* img, uint8_t* out, int vstep, int border,
+                                  int width, int height, int32_t threshold);
+/* pislam::fastExtract<vstep,border,logBucketSize,bucketLimit>(width,height,out,results)
+ * reference Fast.h:196-355.  Writes kp[0..*n) (the entries the reference would append). */
+int pislam_b200_fast_extract(pislam_ctx* ctx, const uint8_t* out, int vstep, int border, int width,
+                             int height, int logBucketSize, int bucketLimit, uint32_t* kp, int cap, int* n);
+/* pislam::harrisScoreSobel<vstep>(img,x,y,threshold)                      reference Harris.h:80-248
+ * `img` points at row 0 of a buffer of `rows` rows; scores npts points (xs[i], ys[i]). */
+int pislam_b200_harris_score_sobel(pislam_ctx* ctx, const uint8_t* img, int vstep, int rows, const int* xs,
+                                   const int* ys, int npts, int32_t threshold, uint8_t* scores);
+/* pislam::orbCentroids<vstep>(img,points)                                 reference Orb.h:80-308
+ * centroids receives (2n+7)&~7 int32 in the reference's [x0 x1 x2 x3 y0 y1 y2 y3] layout. */
+int pislam_b200_orb_centroids(pislam_ctx* ctx, const uint8_t* img, int vstep, int rows, const uint32_t* kp,
+                              int n, int32_t* centroids);
+/* pislam::atan2(xys)                                                      reference Orb.h:310-387
+ * nxys must be a multiple of 8; angles receives nxys/2 bins. */
+int pislam_b200_atan2(pislam_ctx* ctx, const int32_t* xys, int nxys, uint8_t* angles);
+/* pislam::briefDescribe<vstep,words>(img,x,y,rot,descriptor)              reference Brief.h:637-733
+ * rot outside 0..29 leaves `desc` untouched, like the reference's switch. */
+int pislam_b200_brief_describe(pislam_ctx* ctx, const uint8_t* img, int vstep, int rows, int x, int y,
+                               int rot, int words, uint32_t* desc);
+/* pislam::orbCompute<vstep,words>(img,points,descriptors)                 reference Orb.h:396-441
+ * desc receives n*words uint32 (what the reference appends); angles (may be NULL) the n bins. */
+int pislam_b200_orb_compute(pislam_ctx* ctx, const uint8_t* img, int vstep, int rows, const uint32_t* kp,
+                            int n, int words, uint32_t* desc, uint8_t* angles);
+
+/* ---- fused whole-pyramid path (the caller loop of reference demo/demo.cpp:77-101) ----------- */
+typedef struct pislam_pyramid_desc {
+  int vstep;   /* row pitch of the stack in bytes */
+  int nlevels; /* <= PISLAM_MAX_LEVELS */
+  int widths[PISLAM_MAX_LEVELS];
+  int heights[PISLAM_MAX_LEVELS];
+  int row_offsets[PISLAM_MAX_LEVELS]; /* first stack row of each level */
+  int border;                         /* >= 3 (>= 16 when descriptors are wanted) */
+  int fast_threshold;
+  int32_t harris_threshold;
+  int log_bucket_size; /* 0 = no bucketing; fused path supports 0..5 */
+  int bucket_limit;
+  int words; /* 1..8 descriptor words; 0 = keypoints only */
+} pislam_pyramid_desc;
+
+/* Per-frame result record, fixed capacity so that a batch is one contiguous buffer (and one
+ * NCCL all-gather): see pislam_b200_record_bytes / the offsets below.
+ *   uint32 header[16]: [0]=n (keypoints stored, <= cap) [1]=n_total (found) [2..2+nlevels]=index of
+ *                      each level's first keypoint (level_start[nlevels] == n)
+ *   uint32 kp[cap]           encodeFast(score,x,y) with LEVEL-LOCAL y        (Util.h:27-29)
+ *   uint32 desc[cap][words]
+ *   uint8  level[cap]        (padded to 16 bytes)
+ */
+size_t pislam_b200_record_bytes(int cap, int words);
+size_t pislam_b200_record_kp_offset(int cap, int words);
+size_t pislam_b200_record_desc_offset(int cap, int words);
+size_t pislam_b200_record_level_offset(int cap, int words);
+
+/* fastDetect + fastScoreHarris + fastExtract per level, then orbCompute, for `nframes`
+ * independent pyramids of identical geometry; frame f starts at stacks + f*frame_stride.
+ * `stacks` and `records` may each be host or device memory; records receives
+ * nframes * pislam_b200_record_bytes(cap, words) bytes.  Keypoint order and content are the
+ * reference's (with `out` zero-initialised).  Returns PISLAM_ERR_CAPACITY if any frame found
+ * more than `cap` keypoints (records are still valid, truncated to the first `cap`). */
+int pislam_b200_extract_batch(pislam_ctx* ctx, const uint8_t* stacks, size_t frame_stride, int nframes,
+                              const pislam_pyramid_desc* desc, int cap, void* records);
+
+/* Same, issue only: returns after enqueueing on the ctx stream (device-resident inputs and
+ * outputs only).  Capacity overflow is reported by header[1] > header[0]. */
+int pislam_b200_extract_batch_async(pislam_ctx* ctx, const uint8_t* d_stacks, size_t frame_stride,
+                                    int nframes, const pislam_pyramid_desc* desc, int cap, void* d_records);
+
+/* Single pyramid convenience wrapper over extract_batch that scatters the record into the
+ * caller's arrays (host pointers; kp_level / desc may be NULL). */
+int pislam_b200_extract_pyramid(pislam_ctx* ctx, const uint8_t* stack, const pislam_pyramid_desc* desc,
+                                uint32_t* kp, uint8_t* kp_level, uint32_t* descriptors, int cap, int* n);
+
+/* ---- multi-GPU: frames shard one-per-rank, results meet in ONE all-gather --------------------- */
+/* 128-byte ncclUniqueId; create on rank 0, distribute with any host-side channel. */
+int pislam_b200_comm_unique_id(void* id128);
+int pislam_b200_comm_init(pislam_ctx* ctx, int nranks, int rank, const void* id128);
+int pislam_b200_comm_destroy(pislam_ctx* ctx);
+/* extract_batch on this rank's `nframes_local` frames, then a single ncclAllGather of the
+ * fixed-capacity records on the same stream: d_all_records (device) receives
+ * nranks * nframes_local * record_bytes, rank-major.  Stream-ordered; call
+ * pislam_b200_synchronize to wait. */
+int pislam_b200_extract_allgather(pislam_ctx* ctx, const uint8_t* d_stacks, size_t frame_stride,
+                                  int nframes_local, const pislam_pyramid_desc* desc, int cap,
+                                  void* d_all_records);
+
+/* ---- introspection for tests ----------------------------------------------------------------- */
+/* The rotated + clamped rBRIEF pattern the device uses, int8[30][256][4] = (x0,y0,x1,y1)
+ * (reference Brief.h:28-50). */
+int pislam_b200_brief_table(int8_t* table30x256x4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PISLAM_B200_H_ */
