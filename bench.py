@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Headline benchmark: ORB front-end throughput on the VGA 8-level 1.2x stacked pyramid.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--impl ours|reference]
+
+A "step" is one pass of the hot path (FAST-9 -> Harris -> NMS/buckets -> oriented rBRIEF, the caller loop of
+reference demo/demo.cpp:77-101) over a batch of F synthetic stacked pyramids per GPU.  Prints ONE JSON line
+(rank 0).  `value` is device-resident throughput in Mpix/s over level pixels; `e2e` is
+the same metric through the C-ABI call with HOST (pinned) buffers, H2D of the stacks and D2H of the records
+inside the timed region.  `roofline` is for the dominant kernel (front_tile_kernel) and `cpu_baseline` is the
+reference's own CPU implementation timed on this box's host cores on a bounded sample.
+
+--impl reference runs only that CPU arm (oracle/_ref = the reference's headers compiled through the NEON shim;
+falls back to the C oracle port when that library is not present).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from pislam_b200.pyramid import VGA, synthetic_stack  # noqa: E402
+
+METRIC = "orb_frontend_vga_pyramid_throughput"
+UNIT = "Mpix/s"
+WORKLOAD = "VGA 8-level 1.2x stacked pyramid (2210x640), FAST 20 + Harris 2^15 + NMS buckets<4,3> + rBRIEF-256"
+BORDER, FAST_T, HARRIS_T, LOG_BUCKET, BUCKET_LIMIT, WORDS, CAP = 16, 20, 1 << 15, 4, 3, 8, 2048
+N_DISTINCT = 32  # distinct synthetic frames; the batch cycles through them (each copy is its own memory)
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_frames(n):
+    base = [synthetic_stack(VGA, i) for i in range(min(n, N_DISTINCT))]
+    return np.stack([base[i % len(base)] for i in range(n)])
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+class CpuReference:
+    """The reference's CPU implementation of the path on the host cores, one whole pyramid per task."""
+
+    def __init__(self):
+        import oracle_lib
+        self.oracle = oracle_lib.Oracle()
+        self.ref = None
+        if oracle_lib.have_reference():
+            try:
+                self.ref = oracle_lib.Reference()
+            except OSError:
+                self.ref = None
+        self.kind = "reference" if self.ref is not None else "port"
+
+    def _ref_frame(self, stack):
+        ref = self.ref
+        out = np.zeros_like(stack)
+        n = 0
+        kps = []
+        for w, h, r in zip(VGA.widths, VGA.heights, VGA.row_offsets):
+            ref.fast_detect(stack, out, BORDER, w, h, FAST_T, row0=r)
+            ref.fast_score_harris(stack, out, BORDER, w, h, HARRIS_T, row0=r)
+            kp = ref.fast_extract(out, BORDER, w, h, LOG_BUCKET, BUCKET_LIMIT, row0=r, cap=CAP * 4)
+            kps.append((kp & 0xFFFFF000) | ((kp & 0xFFF) + np.uint32(r)))  # demo.cpp:91-97
+        kp = np.concatenate(kps)
+        ref.orb_compute(stack, kp, WORDS)
+        return len(kp)
+
+    def run(self, stacks, nthreads):
+        """Processes every frame once on `nthreads` host threads; returns (seconds, total keypoints)."""
+        nf = stacks.shape[0]
+        t0 = time.perf_counter()
+        if self.ref is None:
+            counts = self.oracle.extract_batch(stacks, VGA.widths, VGA.heights, VGA.row_offsets, nthreads,
+                                               border=BORDER, fast_threshold=FAST_T, harris_threshold=HARRIS_T,
+                                               log_bucket=LOG_BUCKET, bucket_limit=BUCKET_LIMIT, words=WORDS,
+                                               cap=CAP * 4)
+            total = int(counts.sum())
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(nthreads) as ex:  # ctypes releases the GIL inside the reference calls
+                total = sum(ex.map(self._ref_frame, [stacks[f] for f in range(nf)]))
+        return time.perf_counter() - t0, total
+
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cpu = CpuReference()
+    cores = cpu_cores()
+    nf = max(cores * 4, 8)  # a bounded sample of the same workload: a few frames per host thread
+    stacks = make_frames(nf)
+    for _ in range(args.warmup):
+        cpu.run(stacks[:max(cores, 1)], cores)
+    times, kpts = [], 0
+    for _ in range(args.steps):
+        dt, kpts = cpu.run(stacks, cores)
+        times.append(dt)
+    total = sum(times)
+    mpix = VGA.level_pixels * nf * args.steps / total / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mpix, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": nf, "level_pixels_per_frame": VGA.level_pixels,
+                   "keypoints_per_frame": kpts / nf},
+        "keypoints_per_s": kpts * args.steps / total,
+        "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": cores, "kind": cpu.kind,
+                         "sample": "%d frames per step on %d host threads, one pyramid per task" % (nf, cores)},
+        "e2e": {"value": mpix, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+        self.lines = []
+        if self.proc:
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [ln for (t, ln) in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [ln for (_, ln) in self.lines]
+        for ln in rows:
+            f = [x.strip() for x in ln.split(",")]
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except (ValueError, IndexError):
+                continue
+            for k, nm in enumerate(names):
+                if len(f) > 5 + k and f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from pislam_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    F = args.frames
+    desc = api.make_desc(VGA, border=BORDER, fast_threshold=FAST_T, harris_threshold=HARRIS_T,
+                         log_bucket=LOG_BUCKET, bucket_limit=BUCKET_LIMIT, words=WORDS)
+    lay = api.record_layout(CAP, WORDS)
+    rec_bytes = lay["bytes"]
+    frame_bytes = VGA.stack_bytes
+
+    frames = make_frames(F)  # every rank: its own F frames (weak scaling); same synthetic set per rank
+    h_stacks = torch.empty((F, VGA.rows, VGA.vstep), dtype=torch.uint8, pin_memory=True)
+    h_stacks.numpy()[:] = frames
+    h_records = torch.empty(F * rec_bytes, dtype=torch.uint8, pin_memory=True)
+    d_stacks = h_stacks.to("cuda", non_blocking=False)
+    d_all = torch.zeros(world * F * rec_bytes, dtype=torch.uint8, device="cuda")
+    d_records = d_all[rank * F * rec_bytes:(rank + 1) * F * rec_bytes]
+
+    ctx = api.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    gather = "none"
+    if world > 1:
+        try:
+            uid = [api.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            ctx.comm_init(world, rank, uid[0])
+            gather = "ncclAllGather issued by libpislam_b200 on the extraction stream"
+        except Exception as e:  # noqa: BLE001
+            gather = "torch.distributed.all_gather_into_tensor (C-ABI comm unavailable: %s)" % e
+
+    def step_device():
+        """inputs resident in HBM; results (this rank's records, all-gathered when N>1) left in HBM"""
+        if world > 1 and gather.startswith("ncclAllGather"):
+            st = ctx.extract_allgather_ptr(d_stacks.data_ptr(), frame_bytes, F, desc, CAP, d_all.data_ptr())
+        else:
+            st = ctx.extract_batch_ptr(d_stacks.data_ptr(), frame_bytes, F, desc, CAP, d_records.data_ptr(),
+                                       asynchronous=True)
+            if world > 1:
+                with torch.cuda.stream(stream):
+                    dist.all_gather_into_tensor(d_all, d_records)
+        if st != 0:
+            raise RuntimeError("extract failed: %d" % st)
+
+    def step_e2e():
+        """the call a user makes: HOST stacks in, HOST records out (H2D + kernels + D2H inside)"""
+        st = ctx.extract_batch_ptr(h_stacks.data_ptr(), frame_bytes, F, desc, CAP, h_records.data_ptr())
+        if st not in (0, api.PISLAM_ERR_CAPACITY):
+            raise RuntimeError("extract failed: %d" % st)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                d_records.copy_(h_records, non_blocking=True)
+                dist.all_gather_into_tensor(d_all, d_records)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        ctx.synchronize()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """K steps bracketed by barrier + synchronize; device time by CUDA events on the ctx stream."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        t1 = time.perf_counter()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, ctx.launch_count - l0, t0, t1
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_dev, launches, t0, t1 = timed(step_device, args.steps)
+    clocks = sampler.stop(t0, t1) if sampler else None
+
+    # keypoints actually produced (from the records of the last step)
+    hdr = d_records.view(F, rec_bytes)[:, :8].contiguous().cpu().numpy().view(np.uint32)
+    kpts_local = int(hdr[:, 0].sum())
+    overflow = int((hdr[:, 1] > hdr[:, 0]).sum())
+
+    for _ in range(max(args.warmup, 3)):
+        step_e2e()
+    # events on the ctx stream span the H2D copies, the kernels, the D2H copies and any host-side gaps
+    ms_e2e, _, _, _ = timed(step_e2e, args.steps)
+
+    # roofline of the dominant kernel: per-kernel CUDA events (library profiling mode), same inputs
+    roof = None
+    if rank == 0:
+        roof = kernel_roofline(ctx, api, d_stacks, frame_bytes, F, desc, d_records, kpts_local, args.steps)
+
+    if world > 1:
+        t = torch.tensor([kpts_local, overflow], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        kpts_total, overflow = int(t[0].item()), int(t[1].item())
+    else:
+        kpts_total = kpts_local
+
+    if rank == 0:
+        pix = VGA.level_pixels * F * world
+        value = pix * args.steps / (ms_dev * 1e-3) / 1e6
+        e2e_value = pix * args.steps / (ms_e2e * 1e-3) / 1e6
+        cpu = CpuReference()
+        cores = cpu_cores()
+        nf = max(cores * 4, 8)
+        sample = make_frames(nf)
+        cpu.run(sample[:max(cores, 1)], cores)
+        dt, ck = cpu.run(sample, cores)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": F, "level_pixels_per_frame": VGA.level_pixels,
+                       "stack_bytes_per_frame": frame_bytes, "keypoints_per_frame": kpts_total / (F * world),
+                       "l2_policy": "inputs larger than L2 (%d MB of stacks per GPU per step)" % (F * frame_bytes >> 20),
+                       "cap": CAP, "capacity_overflows": overflow, "gather": gather,
+                       "parallelism": "frames sharded one batch per GPU, one all-gather of records" if world > 1
+                       else "single GPU"},
+            "keypoints_per_s": kpts_total * args.steps / (ms_dev * 1e-3),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": F * frame_bytes,
+                    "d2h_bytes_per_step": F * rec_bytes, "ms_per_step": ms_e2e / args.steps,
+                    "keypoints_per_s": kpts_total * args.steps / (ms_e2e * 1e-3)},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": {"value": VGA.level_pixels * nf / dt / 1e6, "unit": UNIT, "cores": cores,
+                             "kind": cpu.kind, "keypoints_per_s": ck / dt,
+                             "sample": "%d frames once on %d host threads, one pyramid per task" % (nf, cores)},
+        }
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def kernel_roofline(ctx, api, d_stacks, frame_bytes, F, desc, d_records, kpts, steps):
+    """Average duration of front_tile_kernel from CUDA events recorded around each of its launches on the
+    ctx stream (pislam_b200_set_profiling), against its algorithmic bytes:
+    every level pixel read once + 4 B per keypoint written."""
+    ctx.set_profiling(True)
+    for _ in range(steps):
+        st = ctx.extract_batch_ptr(d_stacks.data_ptr(), frame_bytes, F, desc, CAP, d_records.data_ptr(),
+                                   asynchronous=True)
+        assert st == 0
+    ms, cnt = ctx.kernel_times()
+    ctx.set_profiling(False)
+    peak, peak_src = measured_peak_gbs()
+    if cnt[0] == 0:
+        return None
+    t_front = ms[0] / cnt[0] * 1e-3
+    alg_bytes = VGA.level_pixels * F + 4 * kpts
+    achieved = alg_bytes / t_front / 1e9
+    return {"kernel": "front_tile_kernel<TMA>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": t_front * 1e3,
+            "launches_timed": int(cnt[0]),
+            "other_kernels_avg_ms": {"order_kernel": ms[1] / max(cnt[1], 1), "orb_kernel": ms[2] / max(cnt[2], 1)}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=256, help="stacked pyramids per step per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,6 +50,15 @@ void* pislam_b200_stream(pislam_ctx* ctx);
 int pislam_b200_synchronize(pislam_ctx* ctx);
 /* Number of kernel launches issued by this ctx since creation (bench.py's gpu_launches). */
 long pislam_b200_launch_count(pislam_ctx* ctx);
+/* Tile staging of the fused kernel: 1 = TMA box loads (default), 0 = plain loads.  The TMA path is also
+ * skipped automatically when vstep / frame_stride / the base address are not multiples of 16 bytes. */
+int pislam_b200_set_tma(pislam_ctx* ctx, int enable);
+/* Per-kernel timing of the fused path (bench.py's roofline): while enabled, CUDA events are recorded on
+ * the ctx stream around every launch of [0] front_tile_kernel, [1] order_kernel, [2] orb_kernel.
+ * pislam_b200_kernel_times synchronises, returns the summed durations (ms) and launch counts since the
+ * last call, and clears them. */
+int pislam_b200_set_profiling(pislam_ctx* ctx, int enable);
+int pislam_b200_kernel_times(pislam_ctx* ctx, double ms[3], long count[3]);
 
 /* ---- literal stages (host buffers) ---------------------------------------------------------- */
 /* pislam::fastDetect<vstep,border>(width,height,img,out,threshold)        reference Fast.h:54-158 */
@@ -89,7 +98,7 @@ typedef struct pislam_pyramid_desc {
   int widths[PISLAM_MAX_LEVELS];
   int heights[PISLAM_MAX_LEVELS];
   int row_offsets[PISLAM_MAX_LEVELS]; /* first stack row of each level */
-  int border;                         /* >= 3 (>= 16 when descriptors are wanted) */
+  int border;                         /* >= 5 (>= 16 when descriptors are wanted) */
   int fast_threshold;
   int32_t harris_threshold;
   int log_bucket_size; /* 0 = no bucketing; fused path supports 0..5 */
@@ -99,7 +108,7 @@ typedef struct pislam_pyramid_desc {
 
 /* Per-frame result record, fixed capacity so that a batch is one contiguous buffer (and one
  * NCCL all-gather): see pislam_b200_record_bytes / the offsets below.
- *   uint32 header[16]: [0]=n (keypoints stored, <= cap) [1]=n_total (found) [2..2+nlevels]=index of
+ *   uint32 header[32]: [0]=n (keypoints stored, <= cap) [1]=n_total (found) [2..2+nlevels]=index of
  *                      each level's first keypoint (level_start[nlevels] == n)
  *   uint32 kp[cap]           encodeFast(score,x,y) with LEVEL-LOCAL y        (Util.h:27-29)
  *   uint32 desc[cap][words]
@@ -115,7 +124,8 @@ size_t pislam_b200_record_level_offset(int cap, int words);
  * `stacks` and `records` may each be host or device memory; records receives
  * nframes * pislam_b200_record_bytes(cap, words) bytes.  Keypoint order and content are the
  * reference's (with `out` zero-initialised).  Returns PISLAM_ERR_CAPACITY if any frame found
- * more than `cap` keypoints (records are still valid, truncated to the first `cap`). */
+ * more than `cap` keypoints (header[1] of that frame then holds the count to size `cap` for; its
+ * stored keypoints are unspecified). */
 int pislam_b200_extract_batch(pislam_ctx* ctx, const uint8_t* stacks, size_t frame_stride, int nframes,
                               const pislam_pyramid_desc* desc, int cap, void* records);
 

@@ -10,9 +10,6 @@ namespace pb {
 // ---------------------------------------------------------------------------------------------
 // FAST-9 (reference Fast.h:54-158).  Ring clockwise from (-1,-3) (Fast.h:66-128).
 // ---------------------------------------------------------------------------------------------
-__device__ __constant__ int8_t c_ring_dx[16] = {-1, 0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2};
-__device__ __constant__ int8_t c_ring_dy[16] = {-3, -3, -3, -2, -1, 0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2};
-
 // >= 9 consecutive set bits in a 16-bit circular word
 __device__ __forceinline__ bool arc9(uint32_t m) {
   uint32_t r = m | (m << 16);
@@ -43,13 +40,6 @@ __device__ __forceinline__ bool fast9_at(Ptr c, int pitch, int t) {
   PB_RING(-3, 1) PB_RING(-3, 0) PB_RING(-3, -1) PB_RING(-2, -2)
 #undef PB_RING
   return arc9(mb & 0xffffu) || arc9(md & 0xffffu);
-}
-
-// SWAR: bit 7 of every byte of the result is (byte of d) > t, t in 0..255 uniform.
-// k7 = (0x7f - (t & 0x7f)) * 0x01010101.
-__device__ __forceinline__ uint32_t bytes_gt(uint32_t d, uint32_t k7, bool t_lt_128) {
-  const uint32_t s = (d & 0x7f7f7f7fu) + k7;
-  return t_lt_128 ? (d | s) : (d & s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -129,7 +119,22 @@ __device__ __host__ __forceinline__ uint32_t decode_y(uint32_t e) { return e & 0
 // Orientation (reference Orb.h:80-308 moments, Orb.h:310-387 angle bin)
 // ---------------------------------------------------------------------------------------------
 // half-width of the moment disc per |dy| (Orb.h:118-126 masks/weights + row macros :163-286)
-__device__ __constant__ int8_t c_disc_u[16] = {15, 15, 15, 15, 15, 15, 14, 14, 13, 13, 12, 11, 10, 9, 7, 5};
+__host__ __device__ __forceinline__ int disc_halfwidth(int ady) {
+  // {15,15,15,15,15,15,14,14,13,13,12,11,10,9,7,5} packed 4 bits each, |dy| = 0 in the low nibble
+  return (int)((0x579abcddeeffffffull >> (4 * ady)) & 15u);
+}
+
+// dot products of four unsigned pixel bytes with signed / unsigned byte weights (IDP.4A)
+__device__ __forceinline__ int32_t dp4a_us(uint32_t pix, uint32_t w_s8, int32_t acc) {
+  int32_t r;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(pix), "r"(w_s8), "r"(acc));
+  return r;
+}
+__device__ __forceinline__ uint32_t dp4a_uu(uint32_t pix, uint32_t w_u8, uint32_t acc) {
+  uint32_t r;
+  asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(pix), "r"(w_u8), "r"(acc));
+  return r;
+}
 
 // ARM FPRecipEstimate (vrecpeq_f32, Orb.h:329): 8 fractional bits, flush-to-zero.
 __device__ __forceinline__ float recpe(float x) {

@@ -1,0 +1,209 @@
+// Descriptor kernels (sm_100a): intensity-centroid orientation + rotated BRIEF, one warp per keypoint.
+//
+// Lane r owns patch row dy = r-15: it loads the row as aligned 32-bit words, funnel-shifts them so that
+// byte 0 is column x-15, and reduces the moments with IDP.4A against a per-|dy| weight table (the disc
+// of Orb.h:118-126).  The aligned rows are then parked in shared memory (row pitch 36 B, conflict-free)
+// and each lane evaluates 8 of the 256 pattern pairs of the keypoint's angle bin -> one descriptor byte.
+// Rules: SURVEY.md section 8a rows O1/O2/O3/B1; nothing here mirrors the reference's NEON code.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "device_ops.cuh"
+#include "front_kernels.cuh"
+
+namespace pb {
+
+constexpr int ORB_WARPS = 8;
+constexpr int PATCH_PITCH_W = 9;  // words per patch row in shared memory (36 bytes)
+
+struct OrbParams {
+  const uint8_t* img;  // frame 0
+  unsigned long long frame_stride;
+  unsigned long long frame_bytes;  // readable bytes per frame (bounds the word loads)
+  int vstep;
+  int words;  // descriptor words per keypoint, 1..8
+  // keypoint source: records (fused path) or a plain array (literal orbCompute)
+  uint8_t* records;
+  RecordLayout rec;
+  int row_off[MAX_LEVELS];
+  const uint32_t* kp;  // literal: n keypoints with y relative to img
+  int n;
+  uint32_t* desc;      // literal: [n][words]
+  uint8_t* angles;     // literal, optional
+  const uint32_t* brief;  // [30][256] (off1 << 16) | off0, byte offsets into the 31 x 36 patch
+};
+
+// 4 unaligned-safe bytes at p as a little-endian word; bytes at or past `end` read as zero
+__device__ __forceinline__ uint32_t load_word_bounded(const uint8_t* p, const uint8_t* end) {
+  if (p + 4 <= end) return *reinterpret_cast<const uint32_t*>(p);
+  uint32_t v = 0;
+  for (int k = 0; k < 4; ++k)
+    if (p + k < end) v |= (uint32_t)p[k] << (8 * k);
+  return v;
+}
+
+// Shared per-CTA tables: s_wx[|dy|][k] = signed byte weights dx (0 outside the disc) of columns 4k..4k+3,
+// s_w1 = 0/1 membership, row pitch 9 words so that the 16 |dy| rows fall into distinct banks.
+__device__ __forceinline__ void build_disc_tables(uint32_t* s_wx, uint32_t* s_w1) {
+  for (int i = threadIdx.x; i < 16 * 8; i += blockDim.x) {
+    const int ady = i >> 3, k = i & 7;
+    const int u = disc_halfwidth(ady);
+    uint32_t wx = 0, w1 = 0;
+    for (int b = 0; b < 4; ++b) {
+      const int dx = 4 * k + b - 15;
+      if (dx >= -u && dx <= u) {
+        wx |= (uint32_t)(uint8_t)(int8_t)dx << (8 * b);
+        w1 |= 1u << (8 * b);
+      }
+    }
+    s_wx[ady * 9 + k] = wx;
+    s_w1[ady * 9 + k] = w1;
+  }
+}
+
+// Loads patch row (lane-15) of the keypoint at (x, y) into w[0..7] (byte j of the row = column x-15+j)
+// and returns this lane's moment contributions.  Lane 31 contributes nothing.
+__device__ __forceinline__ void row_moments(const uint8_t* img, const uint8_t* end, int vstep, int x, int y,
+                                            const uint32_t* s_wx, const uint32_t* s_w1, uint32_t w[8], int32_t& m10,
+                                            int32_t& m01) {
+  const int lane = threadIdx.x & 31;
+  m10 = 0;
+  m01 = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) w[k] = 0;
+  if (lane < 31) {
+    const int dy = lane - 15;
+    const uint8_t* a = img + (size_t)(y + dy) * vstep + (x - 15);
+    const uintptr_t ai = reinterpret_cast<uintptr_t>(a);
+    const uint8_t* a0 = reinterpret_cast<const uint8_t*>(ai & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(ai & 3) * 8;
+    uint32_t r[9];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = load_word_bounded(a0 + 4 * k, end);
+    r[8] = sh ? load_word_bounded(a0 + 32, end) : 0u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = __funnelshift_r(r[k], r[k + 1], sh);
+    const int ady = dy < 0 ? -dy : dy;
+    uint32_t rowsum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      m10 = dp4a_us(w[k], s_wx[ady * 9 + k], m10);
+      rowsum = dp4a_uu(w[k], s_w1[ady * 9 + k], rowsum);
+    }
+    m01 = dy * (int32_t)rowsum;
+  }
+  m10 = __reduce_add_sync(0xffffffffu, m10);
+  m01 = __reduce_add_sync(0xffffffffu, m01);
+}
+
+// One descriptor byte per lane: pairs 8*lane .. 8*lane+7 of angle bin `rot` (Brief.h:28-53, 71-631)
+__device__ __forceinline__ uint32_t brief_byte(const uint8_t* patch, const uint32_t* __restrict__ brief, int rot) {
+  const int lane = threadIdx.x & 31;
+  const uint4* t = reinterpret_cast<const uint4*>(brief + rot * 256 + lane * 8);
+  const uint4 ta = __ldg(t), tb = __ldg(t + 1);
+  const uint32_t e[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+  uint32_t bits = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bits |= (uint32_t)(patch[e[j] & 0xffffu] < patch[e[j] >> 16]) << j;
+  return bits;
+}
+
+// FUSED = 1: keypoints come from the frame records (level-local y + row_off[level]);
+// FUSED = 0: the literal orbCompute / orbCentroids+atan2 on a keypoint array.
+template <int FUSED>
+__global__ void __launch_bounds__(ORB_WARPS * 32) orb_kernel(const __grid_constant__ OrbParams P) {
+  __shared__ uint32_t s_wx[16 * 9], s_w1[16 * 9];
+  __shared__ uint32_t s_patch[ORB_WARPS][32 * PATCH_PITCH_W];
+  build_disc_tables(s_wx, s_w1);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int frame = blockIdx.y;
+  const int i = blockIdx.x * ORB_WARPS + warp;
+  const uint8_t* img = P.img + (size_t)frame * P.frame_stride;
+  const uint8_t* end = img + P.frame_bytes;
+  int n, x, y;
+  uint32_t* desc;
+  if (FUSED) {
+    uint8_t* rec = P.records + (size_t)frame * P.rec.bytes;
+    n = (int)reinterpret_cast<const uint32_t*>(rec)[0];
+    if (i >= n) return;
+    const uint32_t e = reinterpret_cast<const uint32_t*>(rec + P.rec.kp_off)[i];
+    x = (int)decode_x(e);
+    y = (int)decode_y(e) + P.row_off[rec[P.rec.level_off + i]];
+    desc = reinterpret_cast<uint32_t*>(rec + P.rec.desc_off) + (size_t)i * P.words;
+  } else {
+    n = P.n;
+    if (i >= n) return;
+    const uint32_t e = P.kp[i];
+    x = (int)decode_x(e);
+    y = (int)decode_y(e);
+    desc = P.desc ? P.desc + (size_t)i * P.words : nullptr;
+  }
+  uint32_t w[8];
+  int32_t m10, m01;
+  row_moments(img, end, P.vstep, x, y, s_wx, s_w1, w, m10, m01);
+  const int rot = (int)angle_bin(m10, m01);
+  if (!FUSED && P.angles && lane == 0) P.angles[i] = (uint8_t)rot;
+  if (desc == nullptr) return;
+  uint32_t* patch = s_patch[warp];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) patch[lane * PATCH_PITCH_W + k] = w[k];
+  __syncwarp();
+  const uint32_t b = brief_byte(reinterpret_cast<const uint8_t*>(patch), P.brief, rot);
+  if (lane < 4 * P.words) reinterpret_cast<uint8_t*>(desc)[lane] = (uint8_t)b;
+}
+
+// orbCentroids (Orb.h:80-308): moments only, written in the reference's [x0 x1 x2 x3 y0 y1 y2 y3] layout
+__global__ void __launch_bounds__(ORB_WARPS * 32)
+    orb_centroids_kernel(const uint8_t* img, const uint8_t* end, int vstep, const uint32_t* __restrict__ kp, int n,
+                         int32_t* __restrict__ centroids) {
+  __shared__ uint32_t s_wx[16 * 9], s_w1[16 * 9];
+  build_disc_tables(s_wx, s_w1);
+  __syncthreads();
+  const int i = blockIdx.x * ORB_WARPS + (threadIdx.x >> 5);
+  if (i >= n) return;
+  uint32_t w[8];
+  int32_t m10, m01;
+  row_moments(img, end, vstep, (int)decode_x(kp[i]), (int)decode_y(kp[i]), s_wx, s_w1, w, m10, m01);
+  if ((threadIdx.x & 31) == 0) {
+    const int base = (i >> 2) * 8 + (i & 3);
+    centroids[base] = m10;
+    centroids[base + 4] = m01;
+  }
+}
+
+// pislam::atan2 (Orb.h:310-387) on the interleaved centroid layout: group g holds x0..x3 y0..y3
+__global__ void atan2_kernel(const int32_t* __restrict__ xys, int ngroups, uint8_t* __restrict__ angles) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ngroups * 4) return;
+  const int g = i >> 2, k = i & 3;
+  angles[i] = (uint8_t)angle_bin(xys[g * 8 + k], xys[g * 8 + 4 + k]);
+}
+
+// briefDescribe (Brief.h:637-733) for one point and a caller-given rot; one warp.
+__global__ void brief_describe_kernel(const uint8_t* img, const uint8_t* end, int vstep, int x, int y, int rot,
+                                      int words, const uint32_t* __restrict__ brief, uint32_t* __restrict__ desc) {
+  __shared__ uint32_t s_patch[32 * PATCH_PITCH_W];
+  const int lane = threadIdx.x & 31;
+  if (rot < 0 || rot >= 30) return;  // Brief.h:641-732: no case -> descriptor untouched
+  uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (lane < 31) {
+    const uint8_t* a = img + (size_t)(y + lane - 15) * vstep + (x - 15);
+    for (int k = 0; k < 8; ++k) {
+      uint32_t v = 0;
+      for (int b = 0; b < 4; ++b) {
+        const uint8_t* p = a + 4 * k + b;
+        if (4 * k + b < 31 && p < end) v |= (uint32_t)*p << (8 * b);
+      }
+      w[k] = v;
+    }
+  }
+  for (int k = 0; k < 8; ++k) s_patch[lane * PATCH_PITCH_W + k] = w[k];
+  __syncwarp();
+  const uint32_t b = brief_byte(reinterpret_cast<const uint8_t*>(s_patch), brief, rot);
+  if (lane < 4 * words) reinterpret_cast<uint8_t*>(desc)[lane] = (uint8_t)b;
+}
+
+}  // namespace pb

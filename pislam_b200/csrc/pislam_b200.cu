@@ -1,0 +1,878 @@
+// libpislam_b200.so -- host side of the C ABI declared in include/pislam_b200.h.
+//
+// Everything here is plumbing around the sm_100a kernels in front_kernels.cuh / orb_kernels.cuh:
+// device buffers, the tile / piece tables of a pyramid geometry, the TMA tensor map, stream-ordered
+// launches, and (optionally) one ncclAllGather of the fixed-capacity frame records.  There is no CPU
+// implementation of any stage: without a CUDA device pislam_b200_create fails.
+#include "../../include/pislam_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "brief_pattern.h"
+#include "front_kernels.cuh"
+#include "orb_kernels.cuh"
+
+using namespace pb;
+
+#define CK(call)                                  \
+  do {                                            \
+    cudaError_t e_ = (call);                      \
+    if (e_ != cudaSuccess) return -(int)e_;       \
+  } while (0)
+#define CKS(call)                                 \
+  do {                                            \
+    int s_ = (call);                              \
+    if (s_ != PISLAM_OK) return s_;               \
+  } while (0)
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n, bool zero_new = false, cudaStream_t st = nullptr) {
+    if (n <= cap) return cudaSuccess;
+    if (p) {
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) return e;
+      cudaFree(p);
+      p = nullptr;
+      cap = 0;
+    }
+    const size_t want = ((n + (n >> 2) + 4095) & ~(size_t)4095) + 256;  // slack: see load_word_bounded
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) return e;
+    cap = want;
+    if (zero_new) e = cudaMemsetAsync(p, 0, want, st);
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+};
+
+// ---- NCCL through dlopen: the library has no link-time dependency on it --------------------------
+struct NcclUid {
+  char internal[128];
+};
+typedef void* NcclComm;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclUid*) = nullptr;
+  int (*CommInitRank)(NcclComm*, int, NcclUid, int) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
+  bool load() {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) return false;
+    GetUniqueId = reinterpret_cast<int (*)(NcclUid*)>(dlsym(lib, "ncclGetUniqueId"));
+    CommInitRank = reinterpret_cast<int (*)(NcclComm*, int, NcclUid, int)>(dlsym(lib, "ncclCommInitRank"));
+    CommDestroy = reinterpret_cast<int (*)(NcclComm)>(dlsym(lib, "ncclCommDestroy"));
+    AllGather = reinterpret_cast<int (*)(const void*, void*, size_t, int, NcclComm, cudaStream_t)>(
+        dlsym(lib, "ncclAllGather"));
+    return GetUniqueId && CommInitRank && CommDestroy && AllGather;
+  }
+};
+NcclApi g_nccl;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// ---- rotated rBRIEF pattern (reference Brief.h:28-50) ---------------------------------------------
+// theta = rot*pi/15 and its cosf/sinf are folded at compile time in the reference; their fp32 bit
+// patterns are in brief_pattern.h.  Each product and sum is an individually rounded fp32 operation and
+// the rounding is an exact half-away-from-zero roundf, then each coordinate is clamped to [-15, 15].
+int rot_clamp(float v) {
+  const int r = (int)roundf(v);
+  return r < -15 ? -15 : (r > 15 ? 15 : r);
+}
+void build_brief_table(int8_t* t /* [30][256][4] */) {
+  for (int rot = 0; rot < 30; ++rot) {
+    float c, s;
+    memcpy(&c, &PISLAM_BRIEF_COS_BITS[rot], 4);
+    memcpy(&s, &PISLAM_BRIEF_SIN_BITS[rot], 4);
+    for (int k = 0; k < 256; ++k)
+      for (int e = 0; e < 2; ++e) {
+        const float dx = (float)PISLAM_BRIEF_BASE[k][2 * e], dy = (float)PISLAM_BRIEF_BASE[k][2 * e + 1];
+        volatile float cx = c * dx, sy = s * dy, sx = s * dx, cy = c * dy;
+        volatile float rx = cx - sy, ry = sx + cy;
+        t[(rot * 256 + k) * 4 + 2 * e] = (int8_t)rot_clamp(rx);
+        t[(rot * 256 + k) * 4 + 2 * e + 1] = (int8_t)rot_clamp(ry);
+      }
+  }
+}
+
+struct Geometry {
+  pislam_pyramid_desc d;
+  int cap = 0;
+  bool valid = false;
+  int ntiles = 0, npieces = 0;
+  LevelInfo lv[MAX_LEVELS];
+  int piece_base[MAX_LEVELS + 1];
+  long long rows = 0;  // stack rows covered by the levels
+};
+
+bool same_desc(const pislam_pyramid_desc& a, const pislam_pyramid_desc& b) {
+  if (a.vstep != b.vstep || a.nlevels != b.nlevels || a.border != b.border || a.log_bucket_size != b.log_bucket_size)
+    return false;
+  for (int l = 0; l < a.nlevels; ++l)
+    if (a.widths[l] != b.widths[l] || a.heights[l] != b.heights[l] || a.row_offsets[l] != b.row_offsets[l])
+      return false;
+  return true;
+}
+
+}  // namespace
+
+struct pislam_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  long launches = 0;
+  bool use_tma = true;
+  EncodeTiledFn encode = nullptr;
+  uint32_t* d_brief = nullptr;
+  // literal stages
+  DevBuf img, out, kp, desc, aux0, aux1;
+  // fused path
+  Geometry geo;
+  DevBuf tiles, stage, stage_count, piece_cnt, piece_off, stacks, records, hdr;
+  // multi-GPU
+  NcclComm comm = nullptr;
+  int nranks = 1, rank = 0;
+  // optional per-kernel timing (bench.py roofline): events around each fused-path launch
+  bool profiling = false;
+  struct ProfSpan {
+    cudaEvent_t a, b;
+    int which;  // 0 front_tile_kernel, 1 order_kernel, 2 orb_kernel
+  };
+  std::vector<ProfSpan> spans;
+};
+
+namespace {
+
+int check_launch(pislam_ctx* c) {
+  ++c->launches;
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? PISLAM_OK : -(int)e;
+}
+
+// RAII-less span helpers: no-ops unless profiling is on
+void span_begin(pislam_ctx* c, int which) {
+  if (!c->profiling) return;
+  pislam_ctx::ProfSpan s;
+  s.which = which;
+  if (cudaEventCreate(&s.a) != cudaSuccess || cudaEventCreate(&s.b) != cudaSuccess) return;
+  cudaEventRecord(s.a, c->stream);
+  c->spans.push_back(s);
+}
+void span_end(pislam_ctx* c) {
+  if (!c->profiling || c->spans.empty()) return;
+  cudaEventRecord(c->spans.back().b, c->stream);
+}
+
+int set_device(pislam_ctx* c) {
+  CK(cudaSetDevice(c->device));
+  return PISLAM_OK;
+}
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int validate_desc(const pislam_pyramid_desc* d, int cap, bool fused) {
+  if (!d || d->vstep <= 0 || d->nlevels < 1 || d->nlevels > PISLAM_MAX_LEVELS || cap < 1) return PISLAM_ERR_INVALID_ARG;
+  if (d->words < 0 || d->words > 8 || d->bucket_limit < 1 || d->log_bucket_size < 0) return PISLAM_ERR_INVALID_ARG;
+  for (int l = 0; l < d->nlevels; ++l)
+    if (d->widths[l] < 1 || d->heights[l] < 1 || d->widths[l] > d->vstep || d->row_offsets[l] < 0)
+      return PISLAM_ERR_INVALID_ARG;
+  // 12-bit keypoint coordinates (Util.h:27-29); the fused tiles need >= 5 border pixels so that no ring,
+  // Harris window or 3x3 neighbourhood ever leaves the level's own columns, and buckets must tile 128x32.
+  for (int l = 0; l < d->nlevels; ++l)
+    if (d->widths[l] > 4096 || d->heights[l] > 4096) return PISLAM_ERR_UNSUPPORTED;
+  if (fused && d->border < 5) return PISLAM_ERR_UNSUPPORTED;
+  if (d->words > 0 && d->border < 16) return PISLAM_ERR_UNSUPPORTED;
+  if (d->log_bucket_size > 5) return PISLAM_ERR_UNSUPPORTED;
+  return PISLAM_OK;
+}
+
+// Tile + piece tables of a geometry; uploads the tile table when the geometry changed.
+int prepare_geometry(pislam_ctx* c, const pislam_pyramid_desc* d, int cap) {
+  Geometry& g = c->geo;
+  if (g.valid && same_desc(g.d, *d)) {
+    g.d = *d;
+    g.cap = cap;
+    return PISLAM_OK;
+  }
+  g.valid = false;
+  const int B = d->border;
+  const int cb_log = d->log_bucket_size > 0 ? d->log_bucket_size - 1 : 0;
+  const int nseg = NT / (16 << cb_log);
+  std::vector<TileDesc> tiles;
+  int piece = 0;
+  long long rows = 0;
+  for (int l = 0; l < d->nlevels; ++l) {
+    LevelInfo& L = g.lv[l];
+    L.w = d->widths[l];
+    L.h = d->heights[l];
+    L.row_off = d->row_offsets[l];
+    const int iw = L.w - 2 * B, ih = L.h - 2 * B;
+    L.xend = B + 16 * ((iw + 15) / 16);
+    L.ntile_cols = (iw > 0 && ih > 0) ? (iw + TW - 1) / TW : 0;
+    const int ntile_rows = (iw > 0 && ih > 0) ? (ih + TH - 1) / TH : 0;
+    L.piece_base = piece;
+    g.piece_base[l] = piece;
+    for (int tr = 0; tr < ntile_rows; ++tr)
+      for (int tc = 0; tc < L.ntile_cols; ++tc) {
+        TileDesc t;
+        t.level = l;
+        t.x0 = B + tc * TW;
+        t.y0 = B + tr * TH;
+        t.piece0 = piece + tr * nseg * L.ntile_cols + tc;
+        tiles.push_back(t);
+      }
+    piece += ntile_rows * nseg * L.ntile_cols;
+    rows = std::max<long long>(rows, (long long)L.row_off + L.h);
+  }
+  g.piece_base[d->nlevels] = piece;
+  g.ntiles = (int)tiles.size();
+  g.npieces = piece;
+  g.rows = rows;
+  g.d = *d;
+  g.cap = cap;
+  if (g.ntiles > 0) {
+    CK(c->tiles.reserve(tiles.size() * sizeof(TileDesc), false, c->stream));
+    // the table may still be in use by earlier launches on the stream: stream-ordered copy from a
+    // pageable buffer returns once the source has been consumed
+    CK(cudaMemcpyAsync(c->tiles.p, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  g.valid = true;
+  return PISLAM_OK;
+}
+
+int make_tensor_map(pislam_ctx* c, CUtensorMap* m, const uint8_t* base, int vstep, long long rows, int nframes,
+                    size_t frame_stride) {
+  const cuuint64_t dims[3] = {(cuuint64_t)vstep, (cuuint64_t)rows, (cuuint64_t)nframes};
+  const cuuint64_t strides[2] = {(cuuint64_t)vstep, (cuuint64_t)(nframes > 1 ? frame_stride : (size_t)rows * vstep)};
+  const cuuint32_t box[3] = {PIX_W, PIX_H, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? PISLAM_OK : PISLAM_ERR_UNSUPPORTED;
+}
+
+void fill_front_params(const pislam_ctx* c, FrontParams& P, const uint8_t* src, size_t frame_stride) {
+  const Geometry& g = c->geo;
+  memset(&P, 0, sizeof(P));
+  P.src = src;
+  P.frame_stride = frame_stride;
+  P.vstep = g.d.vstep;
+  P.nlevels = g.d.nlevels;
+  for (int l = 0; l < g.d.nlevels; ++l) P.lv[l] = g.lv[l];
+  P.border = g.d.border;
+  P.fast_t = g.d.fast_threshold;
+  P.harris_t = g.d.harris_threshold;
+  P.log_bucket = g.d.log_bucket_size;
+  P.bucket_limit = g.d.bucket_limit;
+  P.cap = g.cap;
+  P.npieces = g.npieces;
+  P.tiles = c->tiles.as<TileDesc>();
+  P.stage = c->stage.as<uint32_t>();
+  P.stage_count = c->stage_count.as<uint32_t>();
+  P.piece_cnt = c->piece_cnt.as<uint32_t>();
+  P.piece_off = c->piece_off.as<uint32_t>();
+}
+
+int reserve_front_scratch(pislam_ctx* c, int nframes) {
+  const Geometry& g = c->geo;
+  CK(c->stage.reserve((size_t)nframes * g.cap * 4, false, c->stream));
+  CK(c->stage_count.reserve((size_t)nframes * 4, true, c->stream));
+  CK(c->piece_cnt.reserve((size_t)nframes * std::max(1, g.npieces) * 4, false, c->stream));
+  CK(c->piece_off.reserve((size_t)nframes * std::max(1, g.npieces) * 4, false, c->stream));
+  return PISLAM_OK;
+}
+
+int launch_order(pislam_ctx* c, int nframes, int words, uint8_t* d_records) {
+  const Geometry& g = c->geo;
+  OrderParams O;
+  memset(&O, 0, sizeof(O));
+  O.nlevels = g.d.nlevels;
+  O.npieces = g.npieces;
+  O.cap = g.cap;
+  for (int l = 0; l <= g.d.nlevels; ++l) O.piece_base[l] = g.piece_base[l];
+  O.stage = c->stage.as<uint32_t>();
+  O.stage_count = c->stage_count.as<uint32_t>();
+  O.piece_cnt = c->piece_cnt.as<uint32_t>();
+  O.piece_off = c->piece_off.as<uint32_t>();
+  O.records = d_records;
+  O.rec = RecordLayout::make(g.cap, words);
+  span_begin(c, 1);
+  order_kernel<<<nframes, ORDER_NT, 0, c->stream>>>(O);
+  span_end(c);
+  return check_launch(c);
+}
+
+// all device pointers; enqueue only
+int enqueue_extract(pislam_ctx* c, const uint8_t* d_stacks, size_t frame_stride, int nframes,
+                    const pislam_pyramid_desc* d, int cap, uint8_t* d_records) {
+  if (!d_stacks || !d_records || nframes < 1 || nframes > 65535) return PISLAM_ERR_INVALID_ARG;
+  CKS(validate_desc(d, cap, true));
+  CKS(prepare_geometry(c, d, cap));
+  const Geometry& g = c->geo;
+  if (nframes > 1 && frame_stride < (size_t)g.rows * d->vstep) return PISLAM_ERR_INVALID_ARG;
+  if (nframes == 1) frame_stride = (size_t)g.rows * d->vstep;
+  CKS(reserve_front_scratch(c, nframes));
+  FrontParams P;
+  fill_front_params(c, P, d_stacks, frame_stride);
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  const bool tma_ok = c->use_tma && c->encode && d->vstep % 16 == 0 && frame_stride % 16 == 0 &&
+                      (reinterpret_cast<uintptr_t>(d_stacks) & 15) == 0 && d->vstep >= 16;
+  if (g.ntiles > 0) {
+    const dim3 grid(g.ntiles, nframes);
+    span_begin(c, 0);
+    if (tma_ok && make_tensor_map(c, &tmap, d_stacks, d->vstep, g.rows, nframes, frame_stride) == PISLAM_OK)
+      front_tile_kernel<MODE_TMA><<<grid, NT, 0, c->stream>>>(P, tmap);
+    else
+      front_tile_kernel<MODE_LDG><<<grid, NT, 0, c->stream>>>(P, tmap);
+    span_end(c);
+    CKS(check_launch(c));
+  }
+  CKS(launch_order(c, nframes, d->words, d_records));
+  if (d->words > 0) {
+    OrbParams Q;
+    memset(&Q, 0, sizeof(Q));
+    Q.img = d_stacks;
+    Q.frame_stride = frame_stride;
+    Q.frame_bytes = (size_t)g.rows * d->vstep;
+    Q.vstep = d->vstep;
+    Q.words = d->words;
+    Q.records = d_records;
+    Q.rec = RecordLayout::make(cap, d->words);
+    for (int l = 0; l < d->nlevels; ++l) Q.row_off[l] = d->row_offsets[l];
+    Q.brief = c->d_brief;
+    const dim3 grid((cap + ORB_WARPS - 1) / ORB_WARPS, nframes);
+    span_begin(c, 2);
+    orb_kernel<1><<<grid, ORB_WARPS * 32, 0, c->stream>>>(Q);
+    span_end(c);
+    CKS(check_launch(c));
+  }
+  return PISLAM_OK;
+}
+
+// after a sync: PISLAM_ERR_CAPACITY if any frame found more keypoints than it stored
+int check_capacity(pislam_ctx* c, const uint8_t* d_records, int nframes, size_t rec_bytes) {
+  std::vector<uint32_t> h((size_t)nframes * 2);
+  CK(cudaMemcpy2DAsync(h.data(), 8, d_records, rec_bytes, 8, nframes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int f = 0; f < nframes; ++f)
+    if (h[2 * f + 1] > h[2 * f]) return PISLAM_ERR_CAPACITY;
+  return PISLAM_OK;
+}
+
+}  // namespace
+
+// ======================================================================================================
+extern "C" {
+
+int pislam_b200_create(pislam_ctx** out, int device, size_t max_stack_bytes, int max_keypoints) {
+  if (!out) return PISLAM_ERR_INVALID_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return PISLAM_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return PISLAM_ERR_NO_DEVICE;  // the kernels are built for sm_100a only
+  pislam_ctx* c = new (std::nothrow) pislam_ctx();
+  if (!c) return PISLAM_ERR_INVALID_ARG;
+  c->device = device;
+  int st = PISLAM_OK;
+  do {
+    cudaError_t e;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { st = -(int)e; break; }
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { st = -(int)e; break; }
+    const char* no_tma = getenv("PISLAM_B200_NO_TMA");
+    c->use_tma = !(no_tma && no_tma[0] == '1');
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      c->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    else
+      cudaGetLastError();
+    // rBRIEF table as byte offsets into the 31-row x 36-byte shared-memory patch
+    std::vector<int8_t> t(30 * 256 * 4);
+    build_brief_table(t.data());
+    std::vector<uint32_t> offs(30 * 256);
+    for (int i = 0; i < 30 * 256; ++i) {
+      const uint32_t o0 = (uint32_t)((t[4 * i + 1] + 15) * (PATCH_PITCH_W * 4) + (t[4 * i + 0] + 15));
+      const uint32_t o1 = (uint32_t)((t[4 * i + 3] + 15) * (PATCH_PITCH_W * 4) + (t[4 * i + 2] + 15));
+      offs[i] = o0 | (o1 << 16);
+    }
+    if ((e = cudaMalloc(&c->d_brief, offs.size() * 4)) != cudaSuccess) { st = -(int)e; break; }
+    if ((e = cudaMemcpy(c->d_brief, offs.data(), offs.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+      st = -(int)e;
+      break;
+    }
+    if (max_stack_bytes && (e = c->stacks.reserve(max_stack_bytes)) != cudaSuccess) { st = -(int)e; break; }
+    (void)max_keypoints;
+  } while (0);
+  if (st != PISLAM_OK) {
+    pislam_b200_destroy(c);
+    return st;
+  }
+  *out = c;
+  return PISLAM_OK;
+}
+
+int pislam_b200_destroy(pislam_ctx* c) {
+  if (!c) return PISLAM_OK;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  DevBuf* bufs[] = {&c->img, &c->out, &c->kp, &c->desc, &c->aux0, &c->aux1, &c->tiles, &c->stage, &c->stage_count,
+                    &c->piece_cnt, &c->piece_off, &c->stacks, &c->records, &c->hdr};
+  for (DevBuf* b : bufs) b->release();
+  if (c->d_brief) cudaFree(c->d_brief);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return PISLAM_OK;
+}
+
+const char* pislam_b200_error_string(int status) {
+  switch (status) {
+    case PISLAM_OK: return "ok";
+    case PISLAM_ERR_INVALID_ARG: return "invalid argument";
+    case PISLAM_ERR_UNSUPPORTED: return "geometry or parameters outside the supported domain";
+    case PISLAM_ERR_CAPACITY: return "keypoint capacity exceeded";
+    case PISLAM_ERR_NO_DEVICE: return "no usable sm_100 CUDA device";
+    default: break;
+  }
+  if (status <= PISLAM_ERR_NCCL) return "NCCL error";
+  if (status < 0) return cudaGetErrorString((cudaError_t)(-status));
+  return "unknown status";
+}
+
+void* pislam_b200_stream(pislam_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int pislam_b200_synchronize(pislam_ctx* c) {
+  if (!c) return PISLAM_ERR_INVALID_ARG;
+  CK(cudaStreamSynchronize(c->stream));
+  return PISLAM_OK;
+}
+
+long pislam_b200_launch_count(pislam_ctx* c) { return c ? c->launches : 0; }
+
+int pislam_b200_set_tma(pislam_ctx* c, int enable) {
+  if (!c) return PISLAM_ERR_INVALID_ARG;
+  c->use_tma = enable != 0;
+  return PISLAM_OK;
+}
+
+int pislam_b200_set_profiling(pislam_ctx* c, int enable) {
+  if (!c) return PISLAM_ERR_INVALID_ARG;
+  c->profiling = enable != 0;
+  return PISLAM_OK;
+}
+
+int pislam_b200_kernel_times(pislam_ctx* c, double ms[3], long count[3]) {
+  if (!c || !ms || !count) return PISLAM_ERR_INVALID_ARG;
+  CKS(set_device(c));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < 3; ++k) {
+    ms[k] = 0.0;
+    count[k] = 0;
+  }
+  for (auto& s : c->spans) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) {
+      ms[s.which] += t;
+      ++count[s.which];
+    } else {
+      cudaGetLastError();
+    }
+    cudaEventDestroy(s.a);
+    cudaEventDestroy(s.b);
+  }
+  c->spans.clear();
+  return PISLAM_OK;
+}
+
+// ---- literal stages -----------------------------------------------------------------------------------
+int pislam_b200_fast_detect(pislam_ctx* c, const uint8_t* img, uint8_t* out, int vstep, int border, int width,
+                            int height, int threshold) {
+  if (!c || !img || !out || vstep < 1 || width < 1 || height < 1 || border < 3 || width > vstep)
+    return PISLAM_ERR_INVALID_ARG;
+  CKS(set_device(c));
+  const int iw = width - 2 * border, ih = height - 2 * border;
+  if (iw <= 0 || ih <= 0) return PISLAM_OK;  // both reference loops are empty
+  const size_t bytes = (size_t)height * vstep;
+  CK(c->img.reserve(bytes, false, c->stream));
+  CK(c->out.reserve(bytes, false, c->stream));
+  CK(cudaMemcpyAsync(c->img.p, img, bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->out.p, out, bytes, cudaMemcpyHostToDevice, c->stream));
+  const int xcount = 16 * ((iw + 15) / 16);
+  fast_detect_kernel<<<dim3((xcount + 127) / 128, ih), 128, 0, c->stream>>>(c->img.as<uint8_t>(), c->out.as<uint8_t>(),
+                                                                            vstep, border, width, height, threshold);
+  CKS(check_launch(c));
+  if (width % 16 != 0) {
+    fast_detect_tail_kernel<<<(ih + 127) / 128, 128, 0, c->stream>>>(c->out.as<uint8_t>(), vstep, border, width, height);
+    CKS(check_launch(c));
+  }
+  CK(cudaMemcpyAsync(out, c->out.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return PISLAM_OK;
+}
+
+int pislam_b200_fast_score_harris(pislam_ctx* c, const uint8_t* img, uint8_t* out, int vstep, int border, int width,
+                                  int height, int32_t threshold) {
+  if (!c || !img || !out || vstep < 1 || width < 1 || height < 1 || border < 3 || width > vstep)
+    return PISLAM_ERR_INVALID_ARG;
+  CKS(set_device(c));
+  const int iw = width - 2 * border, ih = height - 2 * border;
+  if (iw <= 0 || ih <= 0) return PISLAM_OK;
+  const size_t bytes = (size_t)height * vstep;
+  CK(c->img.reserve(bytes, false, c->stream));
+  CK(c->out.reserve(bytes, false, c->stream));
+  CK(cudaMemcpyAsync(c->img.p, img, bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->out.p, out, bytes, cudaMemcpyHostToDevice, c->stream));
+  fast_score_harris_kernel<<<dim3((iw + 127) / 128, ih), 128, 0, c->stream>>>(
+      c->img.as<uint8_t>(), c->out.as<uint8_t>(), vstep, border, width, height, threshold);
+  CKS(check_launch(c));
+  CK(cudaMemcpyAsync(out, c->out.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return PISLAM_OK;
+}
+
+int pislam_b200_fast_extract(pislam_ctx* c, const uint8_t* out, int vstep, int border, int width, int height,
+                             int logBucketSize, int bucketLimit, uint32_t* kp, int cap, int* n) {
+  if (!c || !out || !n || cap < 0 || (cap > 0 && !kp) || vstep < 1 || border < 2 || width > vstep)
+    return PISLAM_ERR_INVALID_ARG;
+  *n = 0;
+  CKS(set_device(c));
+  pislam_pyramid_desc d;
+  memset(&d, 0, sizeof(d));
+  d.vstep = vstep;
+  d.nlevels = 1;
+  d.widths[0] = width;
+  d.heights[0] = height;
+  d.row_offsets[0] = 0;
+  d.border = border;
+  d.log_bucket_size = logBucketSize;
+  d.bucket_limit = bucketLimit;
+  d.words = 0;
+  // capacity: one keypoint per 2x2 cell at most
+  const int iw = width - 2 * border, ih = height - 2 * border;
+  if (iw <= 0 || ih <= 0) return PISLAM_OK;
+  const int maxkp = ((iw + 1) / 2) * ((ih + 1) / 2);
+  const int dcap = std::max(1, std::min(maxkp, std::max(cap, 1)));
+  CKS(validate_desc(&d, dcap, false));
+  CKS(prepare_geometry(c, &d, dcap));
+  const size_t bytes = (size_t)height * vstep;
+  CK(c->out.reserve(bytes, false, c->stream));
+  CK(cudaMemcpyAsync(c->out.p, out, bytes, cudaMemcpyHostToDevice, c->stream));
+  CKS(reserve_front_scratch(c, 1));
+  const RecordLayout rec = RecordLayout::make(dcap, 0);
+  CK(c->records.reserve(rec.bytes, false, c->stream));
+  FrontParams P;
+  fill_front_params(c, P, c->out.as<uint8_t>(), bytes);
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  front_tile_kernel<MODE_SCOREMAP><<<dim3(c->geo.ntiles, 1), NT, 0, c->stream>>>(P, tmap);
+  CKS(check_launch(c));
+  CKS(launch_order(c, 1, 0, c->records.as<uint8_t>()));
+  uint32_t header[2];
+  CK(cudaMemcpyAsync(header, c->records.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *n = (int)header[1];
+  if (header[1] > (uint32_t)cap || header[1] > header[0]) return PISLAM_ERR_CAPACITY;
+  if (header[0])
+    CK(cudaMemcpy(kp, c->records.as<uint8_t>() + rec.kp_off, (size_t)header[0] * 4, cudaMemcpyDeviceToHost));
+  return PISLAM_OK;
+}
+
+int pislam_b200_harris_score_sobel(pislam_ctx* c, const uint8_t* img, int vstep, int rows, const int* xs,
+                                   const int* ys, int npts, int32_t threshold, uint8_t* scores) {
+  if (!c || !img || vstep < 1 || rows < 1 || npts < 0 || (npts && (!xs || !ys || !scores))) return PISLAM_ERR_INVALID_ARG;
+  if (npts == 0) return PISLAM_OK;
+  CKS(set_device(c));
+  const size_t bytes = (size_t)rows * vstep;
+  CK(c->img.reserve(bytes, false, c->stream));
+  CK(c->aux0.reserve((size_t)npts * 8, false, c->stream));
+  CK(c->aux1.reserve((size_t)npts, false, c->stream));
+  int* dx = c->aux0.as<int>();
+  int* dy = dx + npts;
+  CK(cudaMemcpyAsync(c->img.p, img, bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(dx, xs, (size_t)npts * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(dy, ys, (size_t)npts * 4, cudaMemcpyHostToDevice, c->stream));
+  harris_points_kernel<<<(npts + 127) / 128, 128, 0, c->stream>>>(c->img.as<uint8_t>(), vstep, dx, dy, npts, threshold,
+                                                                  c->aux1.as<uint8_t>());
+  CKS(check_launch(c));
+  CK(cudaMemcpyAsync(scores, c->aux1.p, (size_t)npts, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return PISLAM_OK;
+}
+
+int pislam_b200_orb_centroids(pislam_ctx* c, const uint8_t* img, int vstep, int rows, const uint32_t* kp, int n,
+                              int32_t* centroids) {
+  if (!c || !img || vstep < 1 || rows < 1 || n < 0 || (n && (!kp || !centroids))) return PISLAM_ERR_INVALID_ARG;
+  if (n == 0) return PISLAM_OK;
+  CKS(set_device(c));
+  const size_t bytes = (size_t)rows * vstep;
+  const int size = (2 * n + 7) & ~7;  // Orb.h:113-114
+  CK(c->img.reserve(bytes, false, c->stream));
+  CK(c->kp.reserve((size_t)n * 4, false, c->stream));
+  CK(c->aux0.reserve((size_t)size * 4, false, c->stream));
+  CK(cudaMemcpyAsync(c->img.p, img, bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->kp.p, kp, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemsetAsync(c->aux0.p, 0, (size_t)size * 4, c->stream));
+  orb_centroids_kernel<<<(n + ORB_WARPS - 1) / ORB_WARPS, ORB_WARPS * 32, 0, c->stream>>>(
+      c->img.as<uint8_t>(), c->img.as<uint8_t>() + bytes, vstep, c->kp.as<uint32_t>(), n, c->aux0.as<int32_t>());
+  CKS(check_launch(c));
+  CK(cudaMemcpyAsync(centroids, c->aux0.p, (size_t)size * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return PISLAM_OK;
+}
+
+int pislam_b200_atan2(pislam_ctx* c, const int32_t* xys, int nxys, uint8_t* angles) {
+  if (!c || nxys < 0 || (nxys % 8) != 0 || (nxys && (!xys || !angles))) return PISLAM_ERR_INVALID_ARG;
+  if (nxys == 0) return PISLAM_OK;
+  CKS(set_device(c));
+  CK(c->aux0.reserve((size_t)nxys * 4, false, c->stream));
+  CK(c->aux1.reserve((size_t)nxys / 2, false, c->stream));
+  CK(cudaMemcpyAsync(c->aux0.p, xys, (size_t)nxys * 4, cudaMemcpyHostToDevice, c->stream));
+  atan2_kernel<<<(nxys / 2 + 127) / 128, 128, 0, c->stream>>>(c->aux0.as<int32_t>(), nxys / 8, c->aux1.as<uint8_t>());
+  CKS(check_launch(c));
+  CK(cudaMemcpyAsync(angles, c->aux1.p, (size_t)nxys / 2, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return PISLAM_OK;
+}
+
+int pislam_b200_brief_describe(pislam_ctx* c, const uint8_t* img, int vstep, int rows, int x, int y, int rot,
+                               int words, uint32_t* desc) {
+  if (!c || !img || !desc || vstep < 1 || rows < 1 || words < 1 || words > 8) return PISLAM_ERR_INVALID_ARG;
+  if (rot < 0 || rot >= 30) return PISLAM_OK;  // Brief.h:641-732: descriptor untouched
+  if (x < 15 || y < 15 || y + 15 >= rows) return PISLAM_ERR_INVALID_ARG;
+  CKS(set_device(c));
+  const size_t bytes = (size_t)rows * vstep;
+  CK(c->img.reserve(bytes, false, c->stream));
+  CK(c->desc.reserve(32, false, c->stream));
+  CK(cudaMemcpyAsync(c->img.p, img, bytes, cudaMemcpyHostToDevice, c->stream));
+  brief_describe_kernel<<<1, 32, 0, c->stream>>>(c->img.as<uint8_t>(), c->img.as<uint8_t>() + bytes, vstep, x, y, rot,
+                                                 words, c->d_brief, c->desc.as<uint32_t>());
+  CKS(check_launch(c));
+  CK(cudaMemcpyAsync(desc, c->desc.p, (size_t)words * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return PISLAM_OK;
+}
+
+int pislam_b200_orb_compute(pislam_ctx* c, const uint8_t* img, int vstep, int rows, const uint32_t* kp, int n,
+                            int words, uint32_t* desc, uint8_t* angles) {
+  if (!c || !img || vstep < 1 || rows < 1 || n < 0 || words < 1 || words > 8 || (n && (!kp || !desc)))
+    return PISLAM_ERR_INVALID_ARG;
+  if (n == 0) return PISLAM_OK;
+  CKS(set_device(c));
+  const size_t bytes = (size_t)rows * vstep;
+  CK(c->img.reserve(bytes, false, c->stream));
+  CK(c->kp.reserve((size_t)n * 4, false, c->stream));
+  CK(c->desc.reserve((size_t)n * words * 4, false, c->stream));
+  CK(c->aux1.reserve((size_t)n, false, c->stream));
+  CK(cudaMemcpyAsync(c->img.p, img, bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->kp.p, kp, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  OrbParams Q;
+  memset(&Q, 0, sizeof(Q));
+  Q.img = c->img.as<uint8_t>();
+  Q.frame_stride = bytes;
+  Q.frame_bytes = bytes;
+  Q.vstep = vstep;
+  Q.words = words;
+  Q.kp = c->kp.as<uint32_t>();
+  Q.n = n;
+  Q.desc = c->desc.as<uint32_t>();
+  Q.angles = c->aux1.as<uint8_t>();
+  Q.brief = c->d_brief;
+  orb_kernel<0><<<dim3((n + ORB_WARPS - 1) / ORB_WARPS, 1), ORB_WARPS * 32, 0, c->stream>>>(Q);
+  CKS(check_launch(c));
+  CK(cudaMemcpyAsync(desc, c->desc.p, (size_t)n * words * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (angles) CK(cudaMemcpyAsync(angles, c->aux1.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return PISLAM_OK;
+}
+
+// ---- fused path ---------------------------------------------------------------------------------------
+size_t pislam_b200_record_bytes(int cap, int words) { return RecordLayout::make(cap, words).bytes; }
+size_t pislam_b200_record_kp_offset(int cap, int words) { return RecordLayout::make(cap, words).kp_off; }
+size_t pislam_b200_record_desc_offset(int cap, int words) { return RecordLayout::make(cap, words).desc_off; }
+size_t pislam_b200_record_level_offset(int cap, int words) { return RecordLayout::make(cap, words).level_off; }
+
+int pislam_b200_extract_batch_async(pislam_ctx* c, const uint8_t* d_stacks, size_t frame_stride, int nframes,
+                                    const pislam_pyramid_desc* d, int cap, void* d_records) {
+  if (!c) return PISLAM_ERR_INVALID_ARG;
+  CKS(set_device(c));
+  return enqueue_extract(c, d_stacks, frame_stride, nframes, d, cap, static_cast<uint8_t*>(d_records));
+}
+
+int pislam_b200_extract_batch(pislam_ctx* c, const uint8_t* stacks, size_t frame_stride, int nframes,
+                              const pislam_pyramid_desc* d, int cap, void* records) {
+  if (!c || !stacks || !records || nframes < 1) return PISLAM_ERR_INVALID_ARG;
+  CKS(set_device(c));
+  CKS(validate_desc(d, cap, true));
+  long long rows = 0;
+  for (int l = 0; l < d->nlevels; ++l) rows = std::max<long long>(rows, (long long)d->row_offsets[l] + d->heights[l]);
+  const size_t frame_bytes = (size_t)rows * d->vstep;
+  if (nframes == 1) frame_stride = frame_bytes;
+  if (frame_stride < frame_bytes) return PISLAM_ERR_INVALID_ARG;
+  const size_t rec_bytes = RecordLayout::make(cap, d->words).bytes;
+  const uint8_t* d_stacks = stacks;
+  if (!is_device_ptr(stacks)) {
+    const size_t total = (size_t)(nframes - 1) * frame_stride + frame_bytes;
+    CK(c->stacks.reserve(total, false, c->stream));
+    CK(cudaMemcpyAsync(c->stacks.p, stacks, total, cudaMemcpyHostToDevice, c->stream));
+    d_stacks = c->stacks.as<uint8_t>();
+  }
+  uint8_t* d_records = static_cast<uint8_t*>(records);
+  const bool rec_on_host = !is_device_ptr(records);
+  if (rec_on_host) {
+    CK(c->records.reserve(rec_bytes * nframes, false, c->stream));
+    d_records = c->records.as<uint8_t>();
+  }
+  CKS(enqueue_extract(c, d_stacks, frame_stride, nframes, d, cap, d_records));
+  if (rec_on_host) {
+    CK(cudaMemcpyAsync(records, d_records, rec_bytes * nframes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const uint8_t* r = static_cast<const uint8_t*>(records);
+    for (int f = 0; f < nframes; ++f) {
+      const uint32_t* h = reinterpret_cast<const uint32_t*>(r + (size_t)f * rec_bytes);
+      if (h[1] > h[0]) return PISLAM_ERR_CAPACITY;
+    }
+    return PISLAM_OK;
+  }
+  return check_capacity(c, d_records, nframes, rec_bytes);
+}
+
+int pislam_b200_extract_pyramid(pislam_ctx* c, const uint8_t* stack, const pislam_pyramid_desc* d, uint32_t* kp,
+                                uint8_t* kp_level, uint32_t* descriptors, int cap, int* n) {
+  if (!c || !stack || !kp || !n || cap < 1) return PISLAM_ERR_INVALID_ARG;
+  *n = 0;
+  CKS(set_device(c));
+  CKS(validate_desc(d, cap, true));
+  const RecordLayout rec = RecordLayout::make(cap, d->words);
+  CK(c->records.reserve(rec.bytes, false, c->stream));
+  // run with the ctx record buffer as a DEVICE destination, then scatter to the caller's arrays
+  long long rows = 0;
+  for (int l = 0; l < d->nlevels; ++l) rows = std::max<long long>(rows, (long long)d->row_offsets[l] + d->heights[l]);
+  const size_t frame_bytes = (size_t)rows * d->vstep;
+  const uint8_t* d_stack = stack;
+  if (!is_device_ptr(stack)) {
+    CK(c->stacks.reserve(frame_bytes, false, c->stream));
+    CK(cudaMemcpyAsync(c->stacks.p, stack, frame_bytes, cudaMemcpyHostToDevice, c->stream));
+    d_stack = c->stacks.as<uint8_t>();
+  }
+  uint8_t* d_rec = c->records.as<uint8_t>();
+  CKS(enqueue_extract(c, d_stack, frame_bytes, 1, d, cap, d_rec));
+  uint32_t header[REC_HEADER_WORDS];
+  CK(cudaMemcpyAsync(header, d_rec, sizeof(header), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *n = (int)header[1];
+  if (header[1] > header[0]) return PISLAM_ERR_CAPACITY;
+  const size_t m = header[0];
+  if (m) {
+    CK(cudaMemcpyAsync(kp, d_rec + rec.kp_off, m * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (kp_level) CK(cudaMemcpyAsync(kp_level, d_rec + rec.level_off, m, cudaMemcpyDeviceToHost, c->stream));
+    if (descriptors && d->words > 0)
+      CK(cudaMemcpyAsync(descriptors, d_rec + rec.desc_off, m * 4 * d->words, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return PISLAM_OK;
+}
+
+// ---- multi-GPU ----------------------------------------------------------------------------------------
+int pislam_b200_comm_unique_id(void* id128) {
+  if (!id128) return PISLAM_ERR_INVALID_ARG;
+  if (!g_nccl.load()) return PISLAM_ERR_NCCL;
+  NcclUid id;
+  const int r = g_nccl.GetUniqueId(&id);
+  if (r != 0) return PISLAM_ERR_NCCL - r;
+  memcpy(id128, &id, sizeof(id));
+  return PISLAM_OK;
+}
+
+int pislam_b200_comm_init(pislam_ctx* c, int nranks, int rank, const void* id128) {
+  if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return PISLAM_ERR_INVALID_ARG;
+  if (!g_nccl.load()) return PISLAM_ERR_NCCL;
+  CKS(set_device(c));
+  NcclUid id;
+  memcpy(&id, id128, sizeof(id));
+  const int r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+  if (r != 0) return PISLAM_ERR_NCCL - r;
+  c->nranks = nranks;
+  c->rank = rank;
+  return PISLAM_OK;
+}
+
+int pislam_b200_comm_destroy(pislam_ctx* c) {
+  if (!c) return PISLAM_ERR_INVALID_ARG;
+  if (c->comm) {
+    CKS(set_device(c));
+    cudaStreamSynchronize(c->stream);
+    g_nccl.CommDestroy(c->comm);
+    c->comm = nullptr;
+  }
+  c->nranks = 1;
+  c->rank = 0;
+  return PISLAM_OK;
+}
+
+int pislam_b200_extract_allgather(pislam_ctx* c, const uint8_t* d_stacks, size_t frame_stride, int nframes_local,
+                                  const pislam_pyramid_desc* d, int cap, void* d_all_records) {
+  if (!c || !d_all_records || !d) return PISLAM_ERR_INVALID_ARG;
+  if (!c->comm) return PISLAM_ERR_NCCL;
+  CKS(set_device(c));
+  const size_t rec_bytes = RecordLayout::make(cap, d->words).bytes;
+  const size_t slot = rec_bytes * (size_t)nframes_local;
+  // the kernels write this rank's records straight into its slot of the gather buffer (in-place gather)
+  uint8_t* mine = static_cast<uint8_t*>(d_all_records) + slot * (size_t)c->rank;
+  CKS(enqueue_extract(c, d_stacks, frame_stride, nframes_local, d, cap, mine));
+  const int r = g_nccl.AllGather(mine, d_all_records, slot, /*ncclInt8*/ 0, c->comm, c->stream);
+  if (r != 0) return PISLAM_ERR_NCCL - r;
+  return PISLAM_OK;
+}
+
+// ---- introspection ------------------------------------------------------------------------------------
+int pislam_b200_brief_table(int8_t* table30x256x4) {
+  if (!table30x256x4) return PISLAM_ERR_INVALID_ARG;
+  build_brief_table(table30x256x4);
+  return PISLAM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,275 @@
+"""Parity of the CUDA path (through the C ABI, via pislam_b200.api) against the CPU oracle and the
+golden vectors generated from the reference's own headers.  Needs a B200: `pytest -m gpu`.
+
+Bar: bit-exact everywhere (masks, score bytes, ordered keypoint lists, centroids, angle bins, descriptors)."""
+import numpy as np
+import pytest
+
+from pislam_b200 import api
+from pislam_b200.pyramid import FHD, UHD, VGA, PyramidLayout, noise_stack, pyramid_layout, synthetic_stack
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+def first_diff(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    if a.shape != b.shape:
+        return "shape %s vs %s" % (a.shape, b.shape)
+    d = np.flatnonzero(a.ravel() != b.ravel())
+    if len(d) == 0:
+        return "equal"
+    i = int(d[0])
+    return "%d diffs, first at %d: got %s want %s" % (len(d), i, a.ravel()[i], b.ravel()[i])
+
+
+def assert_same(got, want, what):
+    assert np.array_equal(got, want), "%s: %s" % (what, first_diff(got, want))
+
+
+# ------------------------------------------------------------------------------------------ literal stages
+def test_literal_stages_small_golden(ctx, golden):
+    """fastDetect / fastScoreHarris / fastExtract one by one, against reference outputs: ragged widths,
+    borders 16/9/4, thresholds incl. > 127 and negative Harris thresholds."""
+    for i, (vstep, w, h, border, ft, ht) in enumerate(golden["small_params"].tolist()):
+        img = np.ascontiguousarray(golden["small%d_img" % i])
+        out = np.zeros_like(img)
+        ctx.fastDetect(w, h, img, out, ft, border=border)
+        assert_same(out, golden["small%d_mask" % i], "fastDetect case %d" % i)
+        ctx.fastScoreHarris(w, h, img, ht, out, border=border)
+        assert_same(out, golden["small%d_out" % i], "fastScoreHarris case %d" % i)
+        assert_same(ctx.fastExtract(w, h, out, border=border), golden["small%d_kp" % i], "fastExtract case %d" % i)
+        assert_same(ctx.fastExtract(w, h, out, border=border, logBucketSize=3, bucketLimit=2),
+                    golden["small%d_kp_b3_2" % i], "fastExtract<3,2> case %d" % i)
+        assert_same(ctx.fastExtract(w, h, out, border=border, logBucketSize=4, bucketLimit=3),
+                    golden["small%d_kp_b4_3" % i], "fastExtract<4,3> case %d" % i)
+
+
+def test_fast_detect_preserves_untouched_bytes(ctx, golden, oracle):
+    """The reference only writes rows [border,h-border) x the 16-px blocks; everything else in `out` stays."""
+    vstep, w, h, border, ft, ht = golden["small_params"].tolist()[1]
+    img = np.ascontiguousarray(golden["small1_img"])
+    out = np.full_like(img, 0x5a)
+    want = out.copy()
+    oracle.fast_detect(img, want, border, w, h, ft)
+    ctx.fastDetect(w, h, img, out, ft, border=border)
+    assert_same(out, want, "fastDetect on a dirty out buffer")
+
+
+def test_fast_extract_tie_heavy(ctx, golden):
+    for i, (vstep, w, h, border) in enumerate(golden["tie_params"].tolist()):
+        m = np.ascontiguousarray(golden["tie%d_out" % i])
+        assert_same(ctx.fastExtract(w, h, m, border=border), golden["tie%d_kp" % i], "tie %d" % i)
+        assert_same(ctx.fastExtract(w, h, m, border=border, logBucketSize=3, bucketLimit=2),
+                    golden["tie%d_kp_b3_2" % i], "tie %d <3,2>" % i)
+        assert_same(ctx.fastExtract(w, h, m, border=border, logBucketSize=5, bucketLimit=4),
+                    golden["tie%d_kp_b5_4" % i], "tie %d <5,4>" % i)
+
+
+def test_fast_extract_results_append(ctx, golden):
+    m = np.ascontiguousarray(golden["tie0_out"])
+    vstep, w, h, border = golden["tie_params"].tolist()[0]
+    results = [123]
+    kp = ctx.fastExtract(w, h, m, results, border=border)
+    assert results[0] == 123 and results[1:] == [int(v) for v in kp]  # Fast.h:320 appends
+
+
+def test_literal_stages_fixture_levels(ctx, golden, fixture_stack):
+    out = np.zeros_like(fixture_stack)
+    for w, h, r in zip(VGA.widths, VGA.heights, VGA.row_offsets):
+        ctx.fastDetect(w, h, fixture_stack, out, 20, row0=r)
+    nz = np.flatnonzero(out)
+    assert_same(nz, golden["fixture_mask_nz"], "fixture FAST mask")
+    kps = []
+    for w, h, r in zip(VGA.widths, VGA.heights, VGA.row_offsets):
+        ctx.fastScoreHarris(w, h, fixture_stack, 1 << 15, out, row0=r)
+        kps.append(ctx.fastExtract(w, h, out, row0=r))
+    nz = np.flatnonzero(out)
+    assert_same(nz, golden["fixture_out_nz"], "fixture score map support")
+    assert_same(out.ravel()[nz], golden["fixture_out_val"], "fixture score bytes")
+    assert_same(np.concatenate(kps), golden["fixture_kp"], "fixture keypoints")
+
+
+def test_harris_points(ctx, oracle):
+    rng = np.random.Generator(np.random.PCG64(5))
+    img = rng.integers(0, 256, size=(64, 128), dtype=np.uint8)
+    xs = rng.integers(3, 120, size=500)
+    ys = rng.integers(3, 59, size=500)
+    for thr in (-(1 << 31), -1, 0, 1 << 15, (1 << 31) - 1):
+        got = ctx.harrisScoreSobel(img, xs, ys, thr)
+        want = np.asarray([oracle.harris_score_sobel(img, int(x), int(y), thr) for x, y in zip(xs, ys)], np.uint8)
+        assert_same(got, want, "harrisScoreSobel thr %d" % thr)
+
+
+def test_orb_literal(ctx, golden, fixture_stack):
+    img, kp = np.ascontiguousarray(golden["orb_img"]), golden["orb_kp"]
+    assert_same(ctx.orbCentroids(img, kp), golden["orb_centroids"], "orbCentroids")
+    assert_same(ctx.atan2(golden["orb_centroids"]), golden["orb_angles"], "atan2")
+    assert_same(ctx.atan2(golden["angle_xys"]), golden["angle_bins"], "atan2 adversarial")
+    for w in (1, 4, 5, 8):
+        assert_same(ctx.orbCompute(img, kp, words=w), golden["orb_desc_w%d" % w], "orbCompute words=%d" % w)
+    # the whole fixture through the literal orbCompute with demo-style stacked y
+    kps = golden["fixture_kp_stacked"]
+    assert_same(ctx.orbCentroids(fixture_stack, kps), golden["fixture_centroids"], "fixture centroids")
+    d, a = ctx.orbCompute(fixture_stack, kps, want_angles=True)
+    assert_same(a, golden["fixture_angles"][:len(kps)], "fixture angles")
+    assert_same(d, golden["fixture_desc"], "fixture descriptors")
+    descriptors = []
+    ctx.orbCompute(img, kp, descriptors, words=8)
+    assert descriptors == [int(v) for v in golden["orb_desc_w8"].ravel()]  # Orb.h:423 appends
+
+
+def test_brief_describe(ctx, golden, oracle):
+    img = np.ascontiguousarray(golden["orb_img"])
+    for rot in range(30):
+        assert_same(ctx.briefDescribe(img, 40 + rot, 30, rot), oracle.brief_describe(img, 40 + rot, 30, rot),
+                    "briefDescribe rot %d" % rot)
+    for rot in (-1, 30, 255):  # Brief.h:641-732: untouched
+        assert (ctx.briefDescribe(img, 40, 40, rot) == 0xdeadbeef).all()
+    assert_same(api.brief_table(), golden["brief_table"], "brief table")
+
+
+def test_zero_moment_patch_bin(ctx):
+    img = np.full((64, 128), 77, np.uint8)
+    d, a = ctx.orbCompute(img, np.asarray([api.encodeFast(200, 40, 30)], np.uint32), want_angles=True)
+    # a flat patch has m01 == 0 but m10 == 0 too only if the disc is symmetric -- it is; bin 7 (SURVEY spec O2)
+    assert a[0] == 7 and (d == 0).all()
+
+
+# ------------------------------------------------------------------------------------------ fused path
+def oracle_pyramid(oracle, stack, lay, **kw):
+    return oracle.extract_pyramid(stack, lay.widths, lay.heights, lay.row_offsets, **kw)
+
+
+@pytest.mark.parametrize("tma", [True, False])
+def test_fused_fixture(ctx, golden, fixture_stack, oracle, tma):
+    ctx.set_tma(tma)
+    try:
+        kp, lv, desc = ctx.extract_pyramid(fixture_stack, api.make_desc(VGA), cap=4096)
+    finally:
+        ctx.set_tma(True)
+    assert len(kp) == 1754
+    assert_same(kp, golden["fixture_kp"], "fused fixture keypoints (tma=%s)" % tma)
+    assert_same(lv, golden["fixture_kp_level"], "fused fixture levels")
+    assert_same(desc, golden["fixture_desc"], "fused fixture descriptors")
+
+
+@pytest.mark.parametrize("lb,bl", [(4, 3), (4, 5), (3, 2), (5, 4), (1, 1), (2, 1)])
+def test_fused_fixture_bucketed(ctx, golden, fixture_stack, oracle, lb, bl):
+    kp, lv, desc = ctx.extract_pyramid(fixture_stack, api.make_desc(VGA, log_bucket=lb, bucket_limit=bl), cap=8192)
+    okp, olv, odesc = oracle_pyramid(oracle, fixture_stack, VGA, log_bucket=lb, bucket_limit=bl)
+    key = "fixture_kp_b%d_%d" % (lb, bl)
+    if key in golden:
+        assert_same(okp, golden[key], "oracle vs golden")
+    assert_same(kp, okp, "fused bucketed <%d,%d> keypoints" % (lb, bl))
+    assert_same(lv, olv, "levels")
+    assert_same(desc, odesc, "descriptors")
+
+
+@pytest.mark.parametrize("name,lay,seed", [("vga", VGA, 0), ("vga", VGA, 1), ("fhd", FHD, 0)])
+def test_fused_synthetic(ctx, oracle, name, lay, seed):
+    stack = synthetic_stack(lay, seed)
+    for lb, bl in ((0, 5), (4, 3)):
+        kp, lv, desc = ctx.extract_pyramid(stack, api.make_desc(lay, log_bucket=lb, bucket_limit=bl), cap=1 << 15)
+        okp, olv, odesc = oracle_pyramid(oracle, stack, lay, log_bucket=lb, bucket_limit=bl)
+        assert len(okp) > 300
+        assert_same(kp, okp, "%s seed %d <%d,%d> keypoints" % (name, seed, lb, bl))
+        assert_same(lv, olv, "levels")
+        assert_same(desc, odesc, "descriptors")
+
+
+def test_fused_uhd_level_local_y(ctx, oracle):
+    """4K stack is 9946 rows: keypoints stay level-local (12-bit y, Util.h:27-29)."""
+    stack = synthetic_stack(UHD, 0)
+    kp, lv, desc = ctx.extract_pyramid(stack, api.make_desc(UHD, log_bucket=4, bucket_limit=3), cap=1 << 16)
+    okp, olv, odesc = oracle_pyramid(oracle, stack, UHD, log_bucket=4, bucket_limit=3)
+    assert_same(kp, okp, "4K keypoints")
+    assert_same(lv, olv, "4K levels")
+    assert_same(desc, odesc, "4K descriptors")
+
+
+def test_fused_noise_and_thresholds(ctx, oracle):
+    """Adversarial uniform noise: every tile is full of corners, ties and overrun-column flags."""
+    lay = pyramid_layout(640, 480, nlevels=4)
+    stack = noise_stack(lay, 11)
+    for ft, ht, lb, bl in ((40, 1 << 10, 0, 5), (20, 1 << 15, 4, 3), (130, -1, 2, 2), (255, 0, 0, 5)):
+        d = api.make_desc(lay, fast_threshold=ft, harris_threshold=ht, log_bucket=lb, bucket_limit=bl)
+        kp, lv, desc = ctx.extract_pyramid(stack, d, cap=1 << 17)
+        okp, olv, odesc = oracle_pyramid(oracle, stack, lay, fast_threshold=ft, harris_threshold=ht, log_bucket=lb,
+                                         bucket_limit=bl, cap=1 << 17)
+        assert_same(kp, okp, "noise ft=%d keypoints" % ft)
+        assert_same(desc, odesc, "noise descriptors")
+
+
+def test_fused_ragged_geometries(ctx, oracle):
+    """Odd / tiny / non-multiple-of-16 levels, a vstep that is not a multiple of 16 (plain-load staging),
+    levels with no interior, border 16 and larger."""
+    rng = np.random.Generator(np.random.PCG64(3))
+    for vstep, dims, border in ((200, [(200, 77), (167, 64), (33, 40), (139, 33), (50, 31)], 16),
+                                (203, [(203, 90), (170, 75)], 16), (256, [(256, 100), (213, 83)], 20)):
+        offs, r = [], 0
+        for w, h in dims:
+            offs.append(r)
+            r += h
+        lay = PyramidLayout(vstep, [w for w, h in dims], [h for w, h in dims], offs)
+        stack = np.zeros((r, vstep), np.uint8)
+        for (w, h), o in zip(dims, offs):
+            a = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+            stack[o:o + h, :w] = a
+        d = api.make_desc(lay, border=border, fast_threshold=35, harris_threshold=1 << 12)
+        kp, lv, desc = ctx.extract_pyramid(stack, d, cap=1 << 15)
+        okp, olv, odesc = oracle_pyramid(oracle, stack, lay, border=border, fast_threshold=35,
+                                         harris_threshold=1 << 12, cap=1 << 15)
+        assert_same(kp, okp, "ragged vstep %d keypoints" % vstep)
+        assert_same(lv, olv, "levels")
+        assert_same(desc, odesc, "descriptors")
+
+
+def test_fused_batch_and_capacity(ctx, oracle):
+    nf = 5
+    stacks = np.stack([synthetic_stack(VGA, 10 + f) for f in range(nf)])
+    d = api.make_desc(VGA, log_bucket=4, bucket_limit=3)
+    res = ctx.extract_batch(stacks, d, cap=4096)
+    for f in range(nf):
+        okp, olv, odesc = oracle_pyramid(oracle, stacks[f], VGA, log_bucket=4, bucket_limit=3)
+        kp, lv, desc, level_start, n_total = res[f]
+        assert n_total == len(okp)
+        assert_same(kp, okp, "batch frame %d keypoints" % f)
+        assert_same(desc, odesc, "batch frame %d descriptors" % f)
+        want_start = [int((olv < l).sum()) for l in range(9)]
+        assert level_start[:9].tolist() == want_start
+    # capacity overflow is reported, with the count to size for
+    with pytest.raises(api.PislamError) as e:
+        ctx.extract_pyramid(stacks[0], d, cap=100)
+    assert e.value.status == api.PISLAM_ERR_CAPACITY
+    # and the context keeps working afterwards
+    kp, _, _ = ctx.extract_pyramid(stacks[0], d, cap=4096)
+    assert_same(kp, res[0][0], "after overflow")
+
+
+def test_fused_keypoints_only_and_words(ctx, oracle):
+    stack = synthetic_stack(VGA, 2)
+    for words in (0, 1, 4, 8):
+        kp, lv, desc = ctx.extract_pyramid(stack, api.make_desc(VGA, words=words), cap=8192)
+        okp, olv, odesc = oracle_pyramid(oracle, stack, VGA, words=max(words, 1))
+        assert_same(kp, okp, "words=%d keypoints" % words)
+        if words:
+            assert_same(desc, odesc, "words=%d descriptors" % words)
+
+
+def test_argument_errors(ctx):
+    stack = np.zeros((VGA.rows, VGA.vstep), np.uint8)
+    with pytest.raises(api.PislamError) as e:
+        ctx.extract_pyramid(stack, api.make_desc(VGA, border=3), cap=64)
+    assert e.value.status == api.PISLAM_ERR_UNSUPPORTED
+    with pytest.raises(api.PislamError) as e:
+        ctx.extract_pyramid(stack, api.make_desc(VGA, words=9), cap=64)
+    assert e.value.status == api.PISLAM_ERR_INVALID_ARG
+    kp, lv, desc = ctx.extract_pyramid(stack, api.make_desc(VGA), cap=64)  # empty image: no keypoints
+    assert len(kp) == 0
