@@ -25,7 +25,8 @@ namespace pb {
 constexpr int TW = 128;             // tile width  (output pixels)
 constexpr int TH = 32;              // tile height (output pixels)
 constexpr int NT = 256;             // threads per CTA
-constexpr int PIX_W = TW + 16;      // staged pixels: origin (x0-8, y0-4)
+constexpr int PIX_W = TW + 32;      // staged pixels: origin (x0-8-dxo, y0-4); a TMA box must start on a
+                                    // 16-byte boundary of the row, so dxo = (x0-8) & 15 there, 0 otherwise
 constexpr int PIX_H = TH + 10;
 constexpr int SC_W = TW + 8;        // score tile: origin (x0-4, y0-1)
 constexpr int SC_H = TH + 2;
@@ -164,13 +165,15 @@ __global__ void __launch_bounds__(NT) front_tile_kernel(const __grid_constant__ 
   const int x0 = td.x0, y0 = td.y0;
   const int xs_end = L.w - B;  // end of the Harris-scored columns and of the cell origins
   const int ys_end = L.h - B;
+  // column of the staged tile that holds level column x0-8 (a multiple of 4: the host checks border % 4)
+  const int dxo = (MODE == MODE_TMA) ? ((x0 - 8) & 15) : 0;
 
   if (MODE == MODE_TMA) {
     if (tid == 0) {
       mbar_init(&s_bar, 1);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(&s_bar, PIX_H * PIX_W);
-      tma_load_3d(s_pix, &tmap, x0 - 8, L.row_off + y0 - 4, frame, &s_bar);
+      tma_load_3d(s_pix, &tmap, x0 - 8 - dxo, L.row_off + y0 - 4, frame, &s_bar);
     }
   }
   if (tid == 0) {
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(NT) front_tile_kernel(const __grid_constant__ 
         const int y = y0 - 1 + ry, x = x0 - 4 + 4 * wx;
         const int nlo = min(max(xlo - x, 0), 4), nhi = min(max(xhi - x, 0), 4);
         if (y >= B && y < ys_end && nlo < nhi) {
-          const uint32_t* c = pw + (ry + 3) * (PIX_W / 4) + 1 + wx;
+          const uint32_t* c = pw + (ry + 3) * (PIX_W / 4) + (dxo >> 2) + 1 + wx;
           const uint32_t C = c[0];
           const uint32_t E = __funnelshift_r(C, c[1], 24);   // pixels x+3 .. x+6
           const uint32_t W = __funnelshift_r(c[-1], C, 8);   // pixels x-3 .. x
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(NT) front_tile_kernel(const __grid_constant__ 
       for (int k = 0; k < 4; ++k) {
         const int sx = 4 * wx + k;
         bool corner = false;
-        if ((e >> k) & 1u) corner = fast9_at(s_pix + (ry + 3) * PIX_W + 4 + sx, PIX_W, t);
+        if ((e >> k) & 1u) corner = fast9_at(s_pix + (ry + 3) * PIX_W + dxo + 4 + sx, PIX_W, t);
         // columns >= w-border are never scored (Fast.h:172): they keep the raw 0xff flag
         const bool scored = corner && (x0 - 4 + sx) < xs_end;
         if (corner && !scored) s_score[ry * SC_W + sx] = 0xff;
@@ -267,7 +270,7 @@ __global__ void __launch_bounds__(NT) front_tile_kernel(const __grid_constant__ 
     for (int i = tid; i < nh; i += NT) {
       const int idx = s_hlist[i];
       const int ry = idx / SC_W, sx = idx - ry * SC_W;
-      s_score[idx] = harris_code_at(s_pix + (ry + 3) * PIX_W + 4 + sx, PIX_W, P.harris_t);
+      s_score[idx] = harris_code_at(s_pix + (ry + 3) * PIX_W + dxo + 4 + sx, PIX_W, P.harris_t);
     }
     __syncthreads();
   }

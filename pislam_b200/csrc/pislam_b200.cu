@@ -354,7 +354,7 @@ int enqueue_extract(pislam_ctx* c, const uint8_t* d_stacks, size_t frame_stride,
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   const bool tma_ok = c->use_tma && c->encode && d->vstep % 16 == 0 && frame_stride % 16 == 0 &&
-                      (reinterpret_cast<uintptr_t>(d_stacks) & 15) == 0 && d->vstep >= 16;
+                      (reinterpret_cast<uintptr_t>(d_stacks) & 15) == 0 && d->vstep >= 16 && d->border % 4 == 0;
   if (g.ntiles > 0) {
     const dim3 grid(g.ntiles, nframes);
     span_begin(c, 0);
