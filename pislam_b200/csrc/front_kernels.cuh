@@ -143,21 +143,30 @@ __device__ __forceinline__ bool nms_survives(const uint8_t* q, int pitch) {
 // --------------------------------------------------------------------------------------------------
 // The fused tile kernel
 // --------------------------------------------------------------------------------------------------
+// Work lists keep every phase dense: A (SWAR pre-test, all pixels) -> candidates -> B (exact FAST-9)
+// -> corners -> C (Harris code) -> non-zero scores -> D (non-max) -> survivors -> D2 (bucket top-k)
+// -> bitmap over output slots -> E (rank by popcount prefix = the reference's order).
+constexpr int A_COLS = SC_WW;                       // 34 word columns
+constexpr int A_ROWS = 5;                           // rows per phase-A thread
+constexpr int A_GROUPS = (SC_H + A_ROWS - 1) / A_ROWS;  // 7
+static_assert(A_COLS * A_GROUPS <= NT, "phase A: one thread per (word column, row group)");
+static_assert(A_GROUPS * A_ROWS + 6 <= PIX_H + 1, "phase A rows stay inside the staged tile");
+
 template <int MODE>
 __global__ void __launch_bounds__(NT) front_tile_kernel(const __grid_constant__ FrontParams P,
                                                         const __grid_constant__ CUtensorMap tmap) {
   __shared__ __align__(128) uint8_t s_pix[PIX_H * PIX_W];
   __shared__ __align__(16) uint8_t s_score[SC_H * SC_W];
-  __shared__ uint16_t s_cand[NWORD];       // (work item << 4) | 4-bit candidate mask
-  __shared__ uint16_t s_hlist[SC_H * SC_W];  // score-tile indices of FAST corners to be Harris-scored
-  __shared__ uint32_t s_cell[NCELL];
-  __shared__ uint32_t s_cell2[NCELL];
-  __shared__ uint32_t s_tprefix[NT + 1];
-  __shared__ uint32_t s_warp[NT / 32];
-  __shared__ uint32_t s_ncand, s_nh, s_base;
+  __shared__ uint16_t s_listA[SC_H * SC_W];  // FAST candidates (A->B), then non-zero scores (C->D)
+  __shared__ uint16_t s_listB[SC_H * SC_W];  // FAST corners (B->C), then NMS survivors (D->D2)
+  __shared__ __align__(16) uint32_t s_cell[NCELL];
+  __shared__ __align__(16) uint32_t s_cell2[NCELL];
+  __shared__ uint32_t s_bm[NCELL / 32], s_pref[NCELL / 32 + 1];
+  __shared__ uint32_t s_nA, s_nB, s_nC, s_nS, s_base;
   __shared__ __align__(8) uint64_t s_bar;
 
   const int tid = threadIdx.x;
+  const int lane = tid & 31;
   const int frame = blockIdx.y;
   const TileDesc td = P.tiles[blockIdx.x];
   const LevelInfo L = P.lv[td.level];
@@ -165,6 +174,8 @@ __global__ void __launch_bounds__(NT) front_tile_kernel(const __grid_constant__ 
   const int x0 = td.x0, y0 = td.y0;
   const int xs_end = L.w - B;  // end of the Harris-scored columns and of the cell origins
   const int ys_end = L.h - B;
+  const int lb = P.log_bucket;
+  const int cb_log = lb > 0 ? lb - 1 : 0;  // log2(cells per bucket side)
   // column of the staged tile that holds level column x0-8 (a multiple of 4: the host checks border % 4)
   const int dxo = (MODE == MODE_TMA) ? ((x0 - 8) & 15) : 0;
 
@@ -177,23 +188,39 @@ __global__ void __launch_bounds__(NT) front_tile_kernel(const __grid_constant__ 
     }
   }
   if (tid == 0) {
-    s_ncand = 0;
-    s_nh = 0;
+    s_nA = 0;
+    s_nB = 0;
+    s_nC = 0;
+    s_nS = 0;
+  }
+  if (tid < NCELL / 32) s_bm[tid] = 0u;
+  if (lb > 0) {
+    reinterpret_cast<uint4*>(s_cell)[tid] = make_uint4(0u, 0u, 0u, 0u);
+    reinterpret_cast<uint4*>(s_cell2)[tid] = make_uint4(0u, 0u, 0u, 0u);
   }
 
   if (MODE == MODE_SCOREMAP) {
+    __syncthreads();
     // literal fastExtract: the 3x3 neighbourhoods of all cell pixels, straight from the caller's map
     const uint8_t* out = P.src + (size_t)frame * P.frame_stride;
     const int xc_end = B + 2 * ((xs_end - B + 1) / 2), yc_end = B + 2 * ((ys_end - B + 1) / 2);
-    for (int i = tid; i < SC_H * SC_W; i += NT) {
-      const int ry = i / SC_W, sx = i - ry * SC_W;
-      const int x = x0 - 4 + sx, y = y0 - 1 + ry;
-      uint8_t v = 0;
-      if (x >= B - 1 && x <= xc_end && y >= B - 1 && y <= yc_end) v = out[(size_t)y * P.vstep + x];
-      s_score[i] = v;
+    for (int base = 0; base < SC_H * SC_W; base += NT) {
+      const int i = base + tid;
+      bool cand = false;
+      if (i < SC_H * SC_W) {
+        const int ry = i / SC_W, sx = i - ry * SC_W;
+        const int x = x0 - 4 + sx, y = y0 - 1 + ry;
+        uint8_t v = 0;
+        if (x >= B - 1 && x <= xc_end && y >= B - 1 && y <= yc_end) v = out[(size_t)y * P.vstep + x];
+        s_score[i] = v;
+        const int cxp = sx - 4, cyp = ry - 1;
+        cand = v != 0 && cxp >= 0 && cxp < TW && cyp >= 0 && cyp < TH && x0 + (cxp & ~1) < xs_end &&
+               y0 + (cyp & ~1) < ys_end;
+      }
+      warp_push(cand, (uint16_t)i, s_listA, &s_nC);
     }
   } else {
-    for (int i = tid; i < SC_H * SC_W / 4; i += NT) reinterpret_cast<uint32_t*>(s_score)[i] = 0u;
+    for (int i = tid; i < SC_H * SC_W / 16; i += NT) reinterpret_cast<uint4*>(s_score)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (MODE == MODE_LDG) {
       // linear addressing like the reference's img[y][x]; positions outside the frame read as zero
       const uint8_t* img = P.src + (size_t)frame * P.frame_stride;
@@ -207,103 +234,124 @@ __global__ void __launch_bounds__(NT) front_tile_kernel(const __grid_constant__ 
         s_pix[i] = (x >= 0 && x < P.vstep && a >= lo && a < hi) ? lvl[a] : (uint8_t)0;
       }
     }
-  }
-  __syncthreads();
-
-  if (MODE != MODE_SCOREMAP) {
+    __syncthreads();
     if (MODE == MODE_TMA) mbar_wait(&s_bar, 0);
 
     // ---- phase A: SWAR pre-test on the four compass ring pixels ---------------------------------
     // A 9-arc always contains two neighbouring compass points (ring 1,5,9,13), so a corner needs
-    // |p-c| > t on (N or S) and on (E or W).  Exact FAST-9 is decided in phase B on the survivors.
+    // |p-c| > t on (N or S) and on (E or W).  One thread owns a word column (4 pixels) and 5 rows:
+    // V(q) = |I[q+3]-I[q]| > t serves as the S test of row q and the N test of row q+3.
     const int t = P.fast_t & 0xff;  // Fast.h:58 keeps the low byte
-    const uint32_t k7 = (0x7fu - (uint32_t)(t & 0x7f)) * 0x01010101u;
-    const bool t_lt_128 = t < 128;
-    const int xlo = max(B, x0 - 1), xhi = min(L.xend, x0 + TW + 1);  // columns whose flag matters here
-    const uint32_t* pw = reinterpret_cast<const uint32_t*>(s_pix);
-    for (int base = 0; base < NWORD; base += NT) {
-      const int id = base + tid;
-      uint32_t nib = 0;
-      if (id < NWORD) {
-        const int ry = id / SC_WW, wx = id - ry * SC_WW;
-        const int y = y0 - 1 + ry, x = x0 - 4 + 4 * wx;
-        const int nlo = min(max(xlo - x, 0), 4), nhi = min(max(xhi - x, 0), 4);
-        if (y >= B && y < ys_end && nlo < nhi) {
-          const uint32_t* c = pw + (ry + 3) * (PIX_W / 4) + (dxo >> 2) + 1 + wx;
-          const uint32_t C = c[0];
-          const uint32_t E = __funnelshift_r(C, c[1], 24);   // pixels x+3 .. x+6
-          const uint32_t W = __funnelshift_r(c[-1], C, 8);   // pixels x-3 .. x
-          const uint32_t N = c[-3 * (PIX_W / 4)], S = c[3 * (PIX_W / 4)];
-          const uint32_t ns = bytes_gt(__vabsdiffu4(N, C), k7, t_lt_128) | bytes_gt(__vabsdiffu4(S, C), k7, t_lt_128);
+    if (tid < A_COLS * A_GROUPS) {
+      const int g = tid / A_COLS, wx = tid - g * A_COLS;
+      const int r0 = g * A_ROWS;
+      const int x = x0 - 4 + 4 * wx;
+      const int xlo = max(B, x0 - 1), xhi = min(L.xend, x0 + TW + 1);  // columns whose flag matters here
+      const int nlo = min(max(xlo - x, 0), 4), nhi = min(max(xhi - x, 0), 4);
+      uint32_t acc = 0;  // bit 8k+i: pixel k of row r0+i is a candidate
+      if (nlo < nhi) {
+        const uint32_t colmask = (0x01010101u << (8 * nlo)) & (0x01010101u >> (8 * (4 - nhi)));
+        const uint32_t k7 = (0x7fu - (uint32_t)(t & 0x7f)) * 0x01010101u;
+        const bool t_lt_128 = t < 128;
+        const uint32_t* c = reinterpret_cast<const uint32_t*>(s_pix) + r0 * (PIX_W / 4) + (dxo >> 2) + 1 + wx;
+        uint32_t I[A_ROWS + 6];
+#pragma unroll
+        for (int q = 0; q < A_ROWS + 6; ++q) I[q] = c[q * (PIX_W / 4)];
+        uint32_t V[A_ROWS + 3];
+#pragma unroll
+        for (int q = 0; q < A_ROWS + 3; ++q) V[q] = bytes_gt(__vabsdiffu4(I[q + 3], I[q]), k7, t_lt_128);
+#pragma unroll
+        for (int i = 0; i < A_ROWS; ++i) {
+          const int y = y0 - 1 + r0 + i;
+          const uint32_t C = I[i + 3];
+          const uint32_t* cr = c + (i + 3) * (PIX_W / 4);
+          const uint32_t E = __funnelshift_r(C, cr[1], 24);   // pixels x+3 .. x+6
+          const uint32_t W = __funnelshift_r(cr[-1], C, 8);   // pixels x-3 .. x
           const uint32_t ew = bytes_gt(__vabsdiffu4(E, C), k7, t_lt_128) | bytes_gt(__vabsdiffu4(W, C), k7, t_lt_128);
-          uint32_t m = ns & ew & 0x80808080u;
-          m &= (0x80808080u << (8 * nlo)) & (0x80808080u >> (8 * (4 - nhi)));
-          nib = (((m >> 7) * 0x01020408u) >> 24) & 15u;
+          uint32_t m = ((V[i] | V[i + 3]) & ew) >> 7;
+          if (r0 + i >= SC_H || y < B || y >= ys_end) m = 0;
+          acc |= (m & colmask) << i;
         }
       }
-      warp_push(nib != 0, (uint16_t)((id << 4) | nib), s_cand, &s_ncand);
+      // one list reservation per warp for all rows
+      // the last warp of phase A is partial (threads 224..237): its highest lane reserves
+      const int last = min(31, A_COLS * A_GROUPS - 1 - (tid & ~31));
+      const uint32_t amask = 0xffffffffu >> (31 - last);
+      const uint32_t cnt = (uint32_t)__popc(acc);
+      uint32_t incl = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(amask, incl, d);
+        if (lane >= d) incl += o;
+      }
+      uint32_t pos = 0;
+      if (lane == last && incl) pos = atomicAdd(&s_nA, incl);
+      pos = __shfl_sync(amask, pos, last) + incl - cnt;
+      while (acc) {
+        const int b = __ffs(acc) - 1;
+        acc &= acc - 1;
+        s_listA[pos++] = (uint16_t)((r0 + (b & 7)) * SC_W + 4 * wx + (b >> 3));
+      }
     }
     __syncthreads();
 
     // ---- phase B: exact FAST-9 on the candidates (Fast.h:54-158) ---------------------------------
-    const int ncand = (int)s_ncand;
-    for (int base = 0; base < ncand; base += NT) {
+    const int nA = (int)s_nA;
+    for (int base = 0; base < nA; base += NT) {
       const int i = base + tid;
-      const uint32_t e = i < ncand ? s_cand[i] : 0u;
-      const int id = (int)(e >> 4);
-      const int ry = id / SC_WW, wx = id - ry * SC_WW;
-#pragma unroll 1
-      for (int k = 0; k < 4; ++k) {
-        const int sx = 4 * wx + k;
-        bool corner = false;
-        if ((e >> k) & 1u) corner = fast9_at(s_pix + (ry + 3) * PIX_W + dxo + 4 + sx, PIX_W, t);
-        // columns >= w-border are never scored (Fast.h:172): they keep the raw 0xff flag
-        const bool scored = corner && (x0 - 4 + sx) < xs_end;
-        if (corner && !scored) s_score[ry * SC_W + sx] = 0xff;
-        warp_push(scored, (uint16_t)(ry * SC_W + sx), s_hlist, &s_nh);
-      }
+      const int idx = i < nA ? s_listA[i] : 0;
+      const int ry = idx / SC_W, sx = idx - ry * SC_W;
+      const bool corner = i < nA && fast9_at(s_pix + (ry + 3) * PIX_W + dxo + 4 + sx, PIX_W, t);
+      // columns >= w-border are never scored (Fast.h:172): they keep the raw 0xff flag
+      const bool scored = (x0 - 4 + sx) < xs_end;
+      warp_push(corner, (uint16_t)(idx | (scored ? 0 : 0x8000)), s_listB, &s_nB);
     }
     __syncthreads();
 
     // ---- phase C: Harris code of every flagged pixel (Fast.h:166-180, Harris.h:80-248) ------------
-    const int nh = (int)s_nh;
-    for (int i = tid; i < nh; i += NT) {
-      const int idx = s_hlist[i];
+    const int nB = (int)s_nB;
+    for (int base = 0; base < nB; base += NT) {
+      const int i = base + tid;
+      const uint32_t e = i < nB ? s_listB[i] : 0u;
+      const int idx = (int)(e & 0x7fffu);
       const int ry = idx / SC_W, sx = idx - ry * SC_W;
-      s_score[idx] = harris_code_at(s_pix + (ry + 3) * PIX_W + dxo + 4 + sx, PIX_W, P.harris_t);
-    }
-    __syncthreads();
-  }
-
-  // ---- phase D: non-max suppression, one 2x2 cell per slot (Fast.h:228-310) ------------------------
-  // slot order == output order inside a segment: row-major cells (plain) or band / bucket /
-  // position-in-bucket (bucketed, then re-ranked by encoded value in phase D2)
-  const int lb = P.log_bucket;
-  const int cb_log = lb > 0 ? lb - 1 : 0;  // log2(cells per bucket side)
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = tid + NT * j;
-    const int cx = c & (CELLS_X - 1), cy = c >> 6;
-    int slot = c;
-    if (lb > 0) {
-      const int cbm = (1 << cb_log) - 1;
-      slot = ((cy >> cb_log) << (6 + cb_log)) + ((cx >> cb_log) << (2 * cb_log)) + ((cy & cbm) << cb_log) + (cx & cbm);
-    }
-    uint32_t val = 0;
-    const int x = x0 + 2 * cx, y = y0 + 2 * cy;
-    if (x < xs_end && y < ys_end) {
-      const uint8_t* q = s_score + (1 + 2 * cy) * SC_W + 4 + 2 * cx;
-      const uint32_t top = *reinterpret_cast<const uint16_t*>(q);
-      const uint32_t bot = *reinterpret_cast<const uint16_t*>(q + SC_W);
-      if (top | bot) {
-        if (nms_survives(q, SC_W)) val = encode_fast(q[0], x, y);
-        else if (nms_survives(q + 1, SC_W)) val = encode_fast(q[1], x + 1, y);
-        else if (nms_survives(q + SC_W, SC_W)) val = encode_fast(q[SC_W], x, y + 1);
-        else if (nms_survives(q + SC_W + 1, SC_W)) val = encode_fast(q[SC_W + 1], x + 1, y + 1);
+      uint32_t code = 0;
+      if (i < nB) {
+        code = (e & 0x8000u) ? 0xffu
+                             : harris_code_at(s_pix + (ry + 3) * PIX_W + dxo + 4 + sx, PIX_W, P.harris_t);
+        if (code) s_score[idx] = (uint8_t)code;
       }
+      // non-max candidates: non-zero scores on the tile's own cells
+      const int cxp = sx - 4, cyp = ry - 1;
+      const bool cand = code != 0 && cxp >= 0 && cxp < TW && cyp >= 0 && cyp < TH && x0 + (cxp & ~1) < xs_end &&
+                        y0 + (cyp & ~1) < ys_end;
+      warp_push(cand, (uint16_t)idx, s_listA, &s_nC);
     }
-    s_cell[slot] = val;
-    s_cell2[tid + NT * j] = 0u;
+  }
+  __syncthreads();
+
+  // ---- phase D: non-max suppression of the non-zero scores (Fast.h:228-310) -------------------------
+  // slot = position in the reference's output order inside the tile: row-major 2x2 cells (plain) or
+  // band / bucket / position-in-bucket (bucketed; re-ranked by encoded value in phase D2)
+  const int nC = (int)s_nC;
+  for (int base = 0; base < nC; base += NT) {
+    const int i = base + tid;
+    const int idx = i < nC ? s_listA[i] : 0;
+    const int ry = idx / SC_W, sx = idx - ry * SC_W;
+    const uint8_t* q = s_score + idx;
+    const bool surv = i < nC && nms_survives(q, SC_W);
+    int slot = 0;
+    if (surv) {
+      const int cx = (sx - 4) >> 1, cy = (ry - 1) >> 1;
+      slot = cy * CELLS_X + cx;
+      if (lb > 0) {
+        const int cbm = (1 << cb_log) - 1;
+        slot = ((cy >> cb_log) << (6 + cb_log)) + ((cx >> cb_log) << (2 * cb_log)) + ((cy & cbm) << cb_log) + (cx & cbm);
+      }
+      s_cell[slot] = encode_fast(q[0], x0 - 4 + sx, y0 - 1 + ry);
+      if (lb == 0) atomicOr(&s_bm[slot >> 5], 1u << (slot & 31));
+    }
+    if (lb > 0) warp_push(surv, (uint16_t)slot, s_listB, &s_nS);
   }
   __syncthreads();
 
@@ -311,68 +359,69 @@ __global__ void __launch_bounds__(NT) front_tile_kernel(const __grid_constant__ 
   if (lb > 0) {
     // ---- phase D2: per bucket keep the bucket_limit largest encoded values, ascending (Fast.h:321-352)
     const int bslots = 1 << (2 * cb_log);
-#pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
-      const int s = tid + NT * j;
+    const int nS = (int)s_nS;
+    for (int i = tid; i < nS; i += NT) {
+      const int s = s_listB[i];
       const uint32_t v = s_cell[s];
-      if (v != 0u) {
-        const int b0 = s & ~(bslots - 1);
-        int cnt = 0, rank = 0;
-        for (int k = 0; k < bslots; ++k) {
-          const uint32_t o = s_cell[b0 + k];
-          cnt += o != 0u;
-          rank += o > v;
+      const int b0 = s & ~(bslots - 1);
+      int cnt = 1, rank = 0;
+      if (bslots >= 4) {
+        cnt = 0;
+        const uint4* b4 = reinterpret_cast<const uint4*>(s_cell + b0);
+        for (int k = 0; k < (bslots >> 2); ++k) {
+          const uint4 o = b4[k];
+          cnt += (o.x != 0u) + (o.y != 0u) + (o.z != 0u) + (o.w != 0u);
+          rank += (o.x > v) + (o.y > v) + (o.z > v) + (o.w > v);
         }
-        const int kept = min(cnt, P.bucket_limit);
-        if (rank < kept) s_cell2[b0 + (kept - 1 - rank)] = v;
+      }
+      const int kept = min(cnt, P.bucket_limit);
+      if (rank < kept) {
+        const int f = b0 + (kept - 1 - rank);
+        s_cell2[f] = v;
+        atomicOr(&s_bm[f >> 5], 1u << (f & 31));
       }
     }
     __syncthreads();
     cells = s_cell2;
   }
 
-  // ---- phase E: ordered compaction; one staging segment per tile, one piece per (segment, tile) -----
-  uint32_t v4[4];
-  uint32_t mine = 0;
+  // ---- phase E: rank by slot = popcount prefix over the slot bitmap; one staging segment per tile ----
+  if (tid < 32) {
+    const uint32_t pc = (uint32_t)__popc(s_bm[tid]);
+    uint32_t incl = pc;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    v4[j] = cells[4 * tid + j];
-    mine += v4[j] != 0u;
-  }
-  uint32_t incl = mine;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-    if ((tid & 31) >= d) incl += o;
-  }
-  if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
-  __syncthreads();
-  uint32_t wbase = 0;
-#pragma unroll
-  for (int w = 0; w < NT / 32; ++w)
-    if (w < (tid >> 5)) wbase += s_warp[w];
-  const uint32_t excl = wbase + incl - mine;
-  s_tprefix[tid] = excl;
-  if (tid == NT - 1) {
-    const uint32_t total = excl + mine;
-    s_tprefix[NT] = total;
-    s_base = total ? atomicAdd(P.stage_count + frame, total) : 0u;
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    s_pref[tid + 1] = incl;
+    if (tid == 0) s_pref[0] = 0u;
+    if (tid == 31) s_base = incl ? atomicAdd(P.stage_count + frame, incl) : 0u;
   }
   __syncthreads();
   const uint32_t base = s_base;
-  uint32_t* stage = P.stage + (size_t)frame * P.cap;
-  uint32_t pos = base + excl;
+  {
+    const uint32_t w = s_bm[tid >> 3];
+    const int sh = (tid & 7) * 4;
+    uint32_t nib = (w >> sh) & 15u;
+    if (nib) {
+      uint32_t* stage = P.stage + (size_t)frame * P.cap;
+      uint32_t pos = base + s_pref[tid >> 3] + (uint32_t)__popc(w & ((1u << sh) - 1u));
+      const uint4 v = reinterpret_cast<const uint4*>(cells)[tid];
+      const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    if (v4[j] != 0u) {
-      if (pos < (uint32_t)P.cap) stage[pos] = v4[j];
-      ++pos;
+      for (int j = 0; j < 4; ++j)
+        if ((nib >> j) & 1u) {
+          if (pos < (uint32_t)P.cap) stage[pos] = vv[j];
+          ++pos;
+        }
     }
-  // a segment is one cell row (64 slots) or one bucket band (64 << cb_log slots)
-  const int seg_threads = 16 << cb_log;  // threads (4 slots each) per segment
-  const int nseg = NT / seg_threads;
+  }
+  // a segment is one cell row (64 slots = 2 bitmap words) or one bucket band (64 << cb_log slots)
+  const int seg_words = 2 << cb_log;
+  const int nseg = (NCELL / 32) / seg_words;
   if (tid < nseg) {
-    const uint32_t a = s_tprefix[tid * seg_threads], b = s_tprefix[(tid + 1) * seg_threads];
+    const uint32_t a = s_pref[tid * seg_words], b = s_pref[(tid + 1) * seg_words];
     const size_t pi = (size_t)frame * P.npieces + td.piece0 + tid * L.ntile_cols;
     P.piece_cnt[pi] = b - a;
     P.piece_off[pi] = base + a;
