@@ -316,7 +316,8 @@ def run_gpu_arm(args):
                        "parallelism": "frames sharded one batch per GPU, one all-gather of records" if world > 1
                        else "single GPU"},
             "keypoints_per_s": kpts_total * args.steps / (ms_dev * 1e-3),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": F * frame_bytes,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": F * VGA.level_pixels,
+                    "h2d_note": "level pixels only: the padding right of each level is not uploaded",
                     "d2h_bytes_per_step": F * rec_bytes, "ms_per_step": ms_e2e / args.steps,
                     "keypoints_per_s": kpts_total * args.steps / (ms_e2e * 1e-3)},
             "gpu_launches": launches,

@@ -160,6 +160,12 @@ struct pislam_ctx {
   // multi-GPU
   NcclComm comm = nullptr;
   int nranks = 1, rank = 0;
+  // host-buffer batches are pipelined in chunks: H2D (copy_in) | kernels (stream) | D2H (copy_out)
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  static const int kMaxChunks = 8;
+  cudaEvent_t ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {};
+  int pipeline_chunks = 4;
+  bool trim_copies = true;
   // optional per-kernel timing (bench.py roofline): events around each fused-path launch
   bool profiling = false;
   struct ProfSpan {
@@ -387,6 +393,30 @@ int enqueue_extract(pislam_ctx* c, const uint8_t* d_stacks, size_t frame_stride,
   return PISLAM_OK;
 }
 
+// H2D of frames [f0, f0+nf) of a host batch into the same layout on the device.  Only the level pixels travel
+// (one pitched 3-D copy per level): with border >= 5 the fused kernels never read a column >= w of a level,
+// and the padding right of each level is ~1/3 of a stacked pyramid.
+int copy_frames_h2d(pislam_ctx* c, cudaStream_t st, const uint8_t* host, uint8_t* dev, size_t frame_stride,
+                    size_t frame_bytes, int f0, int nf, const pislam_pyramid_desc* d) {
+  if (c->trim_copies && frame_stride % (size_t)d->vstep == 0) {
+    for (int l = 0; l < d->nlevels; ++l) {
+      cudaMemcpy3DParms p;
+      memset(&p, 0, sizeof(p));
+      p.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(host), d->vstep, d->vstep, frame_stride / d->vstep);
+      p.dstPtr = make_cudaPitchedPtr(dev, d->vstep, d->vstep, frame_stride / d->vstep);
+      p.srcPos = make_cudaPos(0, d->row_offsets[l], f0);
+      p.dstPos = p.srcPos;
+      p.extent = make_cudaExtent(d->widths[l], d->heights[l], nf);
+      p.kind = cudaMemcpyHostToDevice;
+      CK(cudaMemcpy3DAsync(&p, st));
+    }
+    return PISLAM_OK;
+  }
+  const size_t bytes = (size_t)(nf - 1) * frame_stride + frame_bytes;
+  CK(cudaMemcpyAsync(dev + (size_t)f0 * frame_stride, host + (size_t)f0 * frame_stride, bytes, cudaMemcpyHostToDevice, st));
+  return PISLAM_OK;
+}
+
 // after a sync: PISLAM_ERR_CAPACITY if any frame found more keypoints than it stored
 int check_capacity(pislam_ctx* c, const uint8_t* d_records, int nframes, size_t rec_bytes) {
   std::vector<uint32_t> h((size_t)nframes * 2);
@@ -421,6 +451,15 @@ int pislam_b200_create(pislam_ctx** out, int device, size_t max_stack_bytes, int
     cudaError_t e;
     if ((e = cudaSetDevice(device)) != cudaSuccess) { st = -(int)e; break; }
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { st = -(int)e; break; }
+    if ((e = cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking)) != cudaSuccess) { st = -(int)e; break; }
+    if ((e = cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking)) != cudaSuccess) { st = -(int)e; break; }
+    for (int i = 0; i < pislam_ctx::kMaxChunks && st == PISLAM_OK; ++i) {
+      if ((e = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming)) != cudaSuccess) st = -(int)e;
+      else if ((e = cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming)) != cudaSuccess) st = -(int)e;
+    }
+    if (st != PISLAM_OK) break;
+    if (const char* ch = getenv("PISLAM_B200_CHUNKS")) c->pipeline_chunks = std::max(1, std::min(atoi(ch), (int)pislam_ctx::kMaxChunks));
+    if (const char* tr = getenv("PISLAM_B200_TRIM")) c->trim_copies = tr[0] != '0';
     const char* no_tma = getenv("PISLAM_B200_NO_TMA");
     c->use_tma = !(no_tma && no_tma[0] == '1');
     void* fn = nullptr;
@@ -459,11 +498,19 @@ int pislam_b200_destroy(pislam_ctx* c) {
   if (!c) return PISLAM_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->copy_in) cudaStreamSynchronize(c->copy_in);
+  if (c->copy_out) cudaStreamSynchronize(c->copy_out);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   DevBuf* bufs[] = {&c->img, &c->out, &c->kp, &c->desc, &c->aux0, &c->aux1, &c->tiles, &c->stage, &c->stage_count,
                     &c->piece_cnt, &c->piece_off, &c->stacks, &c->records, &c->hdr};
   for (DevBuf* b : bufs) b->release();
   if (c->d_brief) cudaFree(c->d_brief);
+  for (int i = 0; i < pislam_ctx::kMaxChunks; ++i) {
+    if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+    if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
+  }
+  if (c->copy_in) cudaStreamDestroy(c->copy_in);
+  if (c->copy_out) cudaStreamDestroy(c->copy_out);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return PISLAM_OK;
@@ -753,23 +800,48 @@ int pislam_b200_extract_batch(pislam_ctx* c, const uint8_t* stacks, size_t frame
   if (nframes == 1) frame_stride = frame_bytes;
   if (frame_stride < frame_bytes) return PISLAM_ERR_INVALID_ARG;
   const size_t rec_bytes = RecordLayout::make(cap, d->words).bytes;
-  const uint8_t* d_stacks = stacks;
-  if (!is_device_ptr(stacks)) {
-    const size_t total = (size_t)(nframes - 1) * frame_stride + frame_bytes;
-    CK(c->stacks.reserve(total, false, c->stream));
-    CK(cudaMemcpyAsync(c->stacks.p, stacks, total, cudaMemcpyHostToDevice, c->stream));
-    d_stacks = c->stacks.as<uint8_t>();
-  }
-  uint8_t* d_records = static_cast<uint8_t*>(records);
+  const bool stacks_on_host = !is_device_ptr(stacks);
   const bool rec_on_host = !is_device_ptr(records);
+  uint8_t* d_records = static_cast<uint8_t*>(records);
   if (rec_on_host) {
     CK(c->records.reserve(rec_bytes * nframes, false, c->stream));
     d_records = c->records.as<uint8_t>();
   }
-  CKS(enqueue_extract(c, d_stacks, frame_stride, nframes, d, cap, d_records));
-  if (rec_on_host) {
-    CK(cudaMemcpyAsync(records, d_records, rec_bytes * nframes, cudaMemcpyDeviceToHost, c->stream));
+  if (stacks_on_host) {
+    // chunked pipeline: copy_in(H2D i+1) || stream(kernels i) || copy_out(D2H i-1)
+    const size_t total = (size_t)(nframes - 1) * frame_stride + frame_bytes;
+    CK(c->stacks.reserve(total, false, c->stream));
+    uint8_t* d_stacks = c->stacks.as<uint8_t>();
+    CKS(prepare_geometry(c, d, cap));
+    const int nchunks = std::max(1, std::min(c->pipeline_chunks, nframes));
+    const int per = (nframes + nchunks - 1) / nchunks;
+    CKS(reserve_front_scratch(c, per));
+    // earlier work on the ctx stream may still read the staging buffer
+    CK(cudaEventRecord(c->ev_k[0], c->stream));
+    CK(cudaStreamWaitEvent(c->copy_in, c->ev_k[0], 0));
+    int i = 0;
+    for (int f0 = 0; f0 < nframes; f0 += per, ++i) {
+      const int nf = std::min(per, nframes - f0);
+      CKS(copy_frames_h2d(c, c->copy_in, stacks, d_stacks, frame_stride, frame_bytes, f0, nf, d));
+      CK(cudaEventRecord(c->ev_in[i], c->copy_in));
+      CK(cudaStreamWaitEvent(c->stream, c->ev_in[i], 0));
+      CKS(enqueue_extract(c, d_stacks + (size_t)f0 * frame_stride, frame_stride, nf, d, cap,
+                          d_records + (size_t)f0 * rec_bytes));
+      if (rec_on_host) {
+        CK(cudaEventRecord(c->ev_k[i], c->stream));
+        CK(cudaStreamWaitEvent(c->copy_out, c->ev_k[i], 0));
+        CK(cudaMemcpyAsync(static_cast<uint8_t*>(records) + (size_t)f0 * rec_bytes, d_records + (size_t)f0 * rec_bytes,
+                           rec_bytes * nf, cudaMemcpyDeviceToHost, c->copy_out));
+      }
+    }
     CK(cudaStreamSynchronize(c->stream));
+    if (rec_on_host) CK(cudaStreamSynchronize(c->copy_out));
+  } else {
+    CKS(enqueue_extract(c, stacks, frame_stride, nframes, d, cap, d_records));
+    if (rec_on_host) CK(cudaMemcpyAsync(records, d_records, rec_bytes * nframes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  if (rec_on_host) {
     const uint8_t* r = static_cast<const uint8_t*>(records);
     for (int f = 0; f < nframes; ++f) {
       const uint32_t* h = reinterpret_cast<const uint32_t*>(r + (size_t)f * rec_bytes);
