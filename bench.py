@@ -327,11 +327,22 @@ def run_gpu_arm(args):
                              "kind": cpu.kind, "keypoints_per_s": ck / dt,
                              "sample": "%d frames once on %d host threads, one pyramid per task" % (nf, cores)},
         }
-        print(json.dumps(line))
-    ctx.close()
+        print(json.dumps(line), flush=True)
+    # teardown order matters: torch may still hold blocks it used on the ctx stream (an ExternalStream);
+    # release them before the stream is destroyed with the context
     if world > 1:
         dist.barrier()
+    barrier()
+    del d_records, d_all, d_stacks, h_stacks, h_records, stream
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    if world > 1:
+        try:
+            ctx.comm_destroy()
+        except Exception:  # noqa: BLE001
+            pass
         dist.destroy_process_group()
+    ctx.close()
 
 
 def kernel_roofline(ctx, api, d_stacks, frame_bytes, F, desc, d_records, kpts, steps):

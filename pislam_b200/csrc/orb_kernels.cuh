@@ -28,6 +28,8 @@ struct OrbParams {
   uint8_t* records;
   RecordLayout rec;
   int row_off[MAX_LEVELS];
+  int nframes;         // fused: frames in this launch; literal: 1
+  int cap;             // fused: record capacity (slots per frame)
   const uint32_t* kp;  // literal: n keypoints with y relative to img
   int n;
   uint32_t* desc;      // literal: [n][words]
@@ -77,14 +79,34 @@ __device__ __forceinline__ void row_moments(const uint8_t* img, const uint8_t* e
     const int dy = lane - 15;
     const uint8_t* a = img + (size_t)(y + dy) * vstep + (x - 15);
     const uintptr_t ai = reinterpret_cast<uintptr_t>(a);
-    const uint8_t* a0 = reinterpret_cast<const uint8_t*>(ai & ~(uintptr_t)3);
-    const uint32_t sh = (uint32_t)(ai & 3) * 8;
-    uint32_t r[9];
+    const uint32_t ob = (uint32_t)(ai & 15);  // byte offset of column x-15 inside its 16-byte chunk
+    const uint8_t* a16 = reinterpret_cast<const uint8_t*>(ai & ~(uintptr_t)15);
+    // three 16-byte loads cover bytes ob .. ob+30 (<= 45): one L1 wavefront per row and load instead of
+    // one per row and 4-byte word
+    uint32_t q[13];
+    if (a16 + 48 <= end) {
+      const uint4* a4 = reinterpret_cast<const uint4*>(a16);
+      const uint4 c0 = __ldg(a4), c1 = __ldg(a4 + 1), c2 = __ldg(a4 + 2);
+      q[0] = c0.x; q[1] = c0.y; q[2] = c0.z; q[3] = c0.w;
+      q[4] = c1.x; q[5] = c1.y; q[6] = c1.z; q[7] = c1.w;
+      q[8] = c2.x; q[9] = c2.y; q[10] = c2.z; q[11] = c2.w;
+    } else {  // the very end of a buffer
 #pragma unroll
-    for (int k = 0; k < 8; ++k) r[k] = load_word_bounded(a0 + 4 * k, end);
-    r[8] = sh ? load_word_bounded(a0 + 32, end) : 0u;
+      for (int k = 0; k < 12; ++k) q[k] = load_word_bounded(a16 + 4 * k, end);
+    }
+    q[12] = 0u;
+    // drop (ob >> 2) leading words, then shift by the remaining (ob & 3) bytes
+    if (ob & 8) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) w[k] = __funnelshift_r(r[k], r[k + 1], sh);
+      for (int k = 0; k < 11; ++k) q[k] = q[k + 2];
+    }
+    if (ob & 4) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) q[k] = q[k + 1];
+    }
+    const uint32_t sh = (ob & 3) * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = __funnelshift_r(q[k], q[k + 1], sh);
     const int ady = dy < 0 ? -dy : dy;
     uint32_t rowsum = 0;
 #pragma unroll
@@ -111,7 +133,9 @@ __device__ __forceinline__ uint32_t brief_byte(const uint8_t* patch, const uint3
 }
 
 // FUSED = 1: keypoints come from the frame records (level-local y + row_off[level]);
-// FUSED = 0: the literal orbCompute / orbCentroids+atan2 on a keypoint array.
+// FUSED = 0: the literal orbCompute on a keypoint array (one frame).
+// Persistent: every warp strides over the (frame, slot) space, so the disc tables are built once per CTA and
+// no CTA is launched for the unused tail of a record.
 template <int FUSED>
 __global__ void __launch_bounds__(ORB_WARPS * 32) orb_kernel(const __grid_constant__ OrbParams P) {
   __shared__ uint32_t s_wx[16 * 9], s_w1[16 * 9];
@@ -119,40 +143,44 @@ __global__ void __launch_bounds__(ORB_WARPS * 32) orb_kernel(const __grid_consta
   build_disc_tables(s_wx, s_w1);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int frame = blockIdx.y;
-  const int i = blockIdx.x * ORB_WARPS + warp;
-  const uint8_t* img = P.img + (size_t)frame * P.frame_stride;
-  const uint8_t* end = img + P.frame_bytes;
-  int n, x, y;
-  uint32_t* desc;
-  if (FUSED) {
-    uint8_t* rec = P.records + (size_t)frame * P.rec.bytes;
-    n = (int)reinterpret_cast<const uint32_t*>(rec)[0];
-    if (i >= n) return;
-    const uint32_t e = reinterpret_cast<const uint32_t*>(rec + P.rec.kp_off)[i];
-    x = (int)decode_x(e);
-    y = (int)decode_y(e) + P.row_off[rec[P.rec.level_off + i]];
-    desc = reinterpret_cast<uint32_t*>(rec + P.rec.desc_off) + (size_t)i * P.words;
-  } else {
-    n = P.n;
-    if (i >= n) return;
-    const uint32_t e = P.kp[i];
-    x = (int)decode_x(e);
-    y = (int)decode_y(e);
-    desc = P.desc ? P.desc + (size_t)i * P.words : nullptr;
-  }
-  uint32_t w[8];
-  int32_t m10, m01;
-  row_moments(img, end, P.vstep, x, y, s_wx, s_w1, w, m10, m01);
-  const int rot = (int)angle_bin(m10, m01);
-  if (!FUSED && P.angles && lane == 0) P.angles[i] = (uint8_t)rot;
-  if (desc == nullptr) return;
+  const long long nwarps = (long long)gridDim.x * ORB_WARPS;
+  const int cap = FUSED ? P.cap : P.n;
+  const long long nslots = (long long)P.nframes * cap;
   uint32_t* patch = s_patch[warp];
+  for (long long slot = (long long)blockIdx.x * ORB_WARPS + warp; slot < nslots; slot += nwarps) {
+    const int frame = (int)(slot / cap);
+    const int i = (int)(slot - (long long)frame * cap);
+    const uint8_t* img = P.img + (size_t)frame * P.frame_stride;
+    const uint8_t* end = img + P.frame_bytes;
+    int x, y;
+    uint32_t* desc;
+    if (FUSED) {
+      uint8_t* rec = P.records + (size_t)frame * P.rec.bytes;
+      const int n = (int)__ldg(reinterpret_cast<const uint32_t*>(rec));
+      if (i >= n) continue;
+      const uint32_t e = __ldg(reinterpret_cast<const uint32_t*>(rec + P.rec.kp_off) + i);
+      x = (int)decode_x(e);
+      y = (int)decode_y(e) + P.row_off[rec[P.rec.level_off + i]];
+      desc = reinterpret_cast<uint32_t*>(rec + P.rec.desc_off) + (size_t)i * P.words;
+    } else {
+      const uint32_t e = P.kp[i];
+      x = (int)decode_x(e);
+      y = (int)decode_y(e);
+      desc = P.desc ? P.desc + (size_t)i * P.words : nullptr;
+    }
+    uint32_t w[8];
+    int32_t m10, m01;
+    row_moments(img, end, P.vstep, x, y, s_wx, s_w1, w, m10, m01);
+    const int rot = (int)angle_bin(m10, m01);
+    if (!FUSED && P.angles && lane == 0) P.angles[i] = (uint8_t)rot;
+    if (desc == nullptr) continue;
+    __syncwarp();  // the previous keypoint's pattern reads are done
 #pragma unroll
-  for (int k = 0; k < 8; ++k) patch[lane * PATCH_PITCH_W + k] = w[k];
-  __syncwarp();
-  const uint32_t b = brief_byte(reinterpret_cast<const uint8_t*>(patch), P.brief, rot);
-  if (lane < 4 * P.words) reinterpret_cast<uint8_t*>(desc)[lane] = (uint8_t)b;
+    for (int k = 0; k < 8; ++k) patch[lane * PATCH_PITCH_W + k] = w[k];
+    __syncwarp();
+    const uint32_t b = brief_byte(reinterpret_cast<const uint8_t*>(patch), P.brief, rot);
+    if (lane < 4 * P.words) reinterpret_cast<uint8_t*>(desc)[lane] = (uint8_t)b;
+  }
 }
 
 // orbCentroids (Orb.h:80-308): moments only, written in the reference's [x0 x1 x2 x3 y0 y1 y2 y3] layout

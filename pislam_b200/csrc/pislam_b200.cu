@@ -149,6 +149,7 @@ struct pislam_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   long launches = 0;
+  int num_sms = 148;
   bool use_tma = true;
   EncodeTiledFn encode = nullptr;
   uint32_t* d_brief = nullptr;
@@ -384,7 +385,10 @@ int enqueue_extract(pislam_ctx* c, const uint8_t* d_stacks, size_t frame_stride,
     Q.rec = RecordLayout::make(cap, d->words);
     for (int l = 0; l < d->nlevels; ++l) Q.row_off[l] = d->row_offsets[l];
     Q.brief = c->d_brief;
-    const dim3 grid((cap + ORB_WARPS - 1) / ORB_WARPS, nframes);
+    Q.nframes = nframes;
+    Q.cap = cap;
+    const long long want = ((long long)nframes * cap + ORB_WARPS - 1) / ORB_WARPS;
+    const dim3 grid((unsigned)std::min<long long>(want, (long long)c->num_sms * 8));
     span_begin(c, 2);
     orb_kernel<1><<<grid, ORB_WARPS * 32, 0, c->stream>>>(Q);
     span_end(c);
@@ -446,6 +450,7 @@ int pislam_b200_create(pislam_ctx** out, int device, size_t max_stack_bytes, int
   pislam_ctx* c = new (std::nothrow) pislam_ctx();
   if (!c) return PISLAM_ERR_INVALID_ARG;
   c->device = device;
+  c->num_sms = prop.multiProcessorCount;
   int st = PISLAM_OK;
   do {
     cudaError_t e;
@@ -768,7 +773,9 @@ int pislam_b200_orb_compute(pislam_ctx* c, const uint8_t* img, int vstep, int ro
   Q.desc = c->desc.as<uint32_t>();
   Q.angles = c->aux1.as<uint8_t>();
   Q.brief = c->d_brief;
-  orb_kernel<0><<<dim3((n + ORB_WARPS - 1) / ORB_WARPS, 1), ORB_WARPS * 32, 0, c->stream>>>(Q);
+  Q.nframes = 1;
+  Q.cap = n;
+  orb_kernel<0><<<dim3(std::min((n + ORB_WARPS - 1) / ORB_WARPS, c->num_sms * 8)), ORB_WARPS * 32, 0, c->stream>>>(Q);
   CKS(check_launch(c));
   CK(cudaMemcpyAsync(desc, c->desc.p, (size_t)n * words * 4, cudaMemcpyDeviceToHost, c->stream));
   if (angles) CK(cudaMemcpyAsync(angles, c->aux1.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
