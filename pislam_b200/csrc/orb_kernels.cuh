@@ -34,7 +34,8 @@ struct OrbParams {
   int n;
   uint32_t* desc;      // literal: [n][words]
   uint8_t* angles;     // literal, optional
-  const uint32_t* brief;  // [30][256] (off1 << 16) | off0, byte offsets into the 31 x 36 patch
+  const uint32_t* brief;    // [30][256] (off1 << 16) | off0, byte offsets into the 31 x 36-byte patch
+  const uint32_t* brief48;  // same for the 48-byte row pitch of the TMA patch buffers
 };
 
 // 4 unaligned-safe bytes at p as a little-endian word; bytes at or past `end` read as zero
@@ -65,48 +66,28 @@ __device__ __forceinline__ void build_disc_tables(uint32_t* s_wx, uint32_t* s_w1
   }
 }
 
-// Loads patch row (lane-15) of the keypoint at (x, y) into w[0..7] (byte j of the row = column x-15+j)
-// and returns this lane's moment contributions.  Lane 31 contributes nothing.
-__device__ __forceinline__ void row_moments(const uint8_t* img, const uint8_t* end, int vstep, int x, int y,
-                                            const uint32_t* s_wx, const uint32_t* s_w1, uint32_t w[8], int32_t& m10,
-                                            int32_t& m01) {
+// q[0..11] hold the 48 bytes of this lane's patch row starting at its 16-byte chunk; column x-15 is byte `ob`.
+// Produces w[0..7] (byte j = column x-15+j) and this warp's moments.  Lane 31 contributes nothing.
+__device__ __forceinline__ void moments_from_chunks(uint32_t q[13], uint32_t ob, const uint32_t* s_wx,
+                                                    const uint32_t* s_w1, uint32_t w[8], int32_t& m10, int32_t& m01) {
   const int lane = threadIdx.x & 31;
   m10 = 0;
   m01 = 0;
+  q[12] = 0u;
+  // drop (ob >> 2) leading words, then shift by the remaining (ob & 3) bytes
+  if (ob & 8) {
 #pragma unroll
-  for (int k = 0; k < 8; ++k) w[k] = 0;
+    for (int k = 0; k < 11; ++k) q[k] = q[k + 2];
+  }
+  if (ob & 4) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) q[k] = q[k + 1];
+  }
+  const uint32_t sh = (ob & 3) * 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) w[k] = __funnelshift_r(q[k], q[k + 1], sh);
   if (lane < 31) {
     const int dy = lane - 15;
-    const uint8_t* a = img + (size_t)(y + dy) * vstep + (x - 15);
-    const uintptr_t ai = reinterpret_cast<uintptr_t>(a);
-    const uint32_t ob = (uint32_t)(ai & 15);  // byte offset of column x-15 inside its 16-byte chunk
-    const uint8_t* a16 = reinterpret_cast<const uint8_t*>(ai & ~(uintptr_t)15);
-    // three 16-byte loads cover bytes ob .. ob+30 (<= 45): one L1 wavefront per row and load instead of
-    // one per row and 4-byte word
-    uint32_t q[13];
-    if (a16 + 48 <= end) {
-      const uint4* a4 = reinterpret_cast<const uint4*>(a16);
-      const uint4 c0 = __ldg(a4), c1 = __ldg(a4 + 1), c2 = __ldg(a4 + 2);
-      q[0] = c0.x; q[1] = c0.y; q[2] = c0.z; q[3] = c0.w;
-      q[4] = c1.x; q[5] = c1.y; q[6] = c1.z; q[7] = c1.w;
-      q[8] = c2.x; q[9] = c2.y; q[10] = c2.z; q[11] = c2.w;
-    } else {  // the very end of a buffer
-#pragma unroll
-      for (int k = 0; k < 12; ++k) q[k] = load_word_bounded(a16 + 4 * k, end);
-    }
-    q[12] = 0u;
-    // drop (ob >> 2) leading words, then shift by the remaining (ob & 3) bytes
-    if (ob & 8) {
-#pragma unroll
-      for (int k = 0; k < 11; ++k) q[k] = q[k + 2];
-    }
-    if (ob & 4) {
-#pragma unroll
-      for (int k = 0; k < 9; ++k) q[k] = q[k + 1];
-    }
-    const uint32_t sh = (ob & 3) * 8;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) w[k] = __funnelshift_r(q[k], q[k + 1], sh);
     const int ady = dy < 0 ? -dy : dy;
     uint32_t rowsum = 0;
 #pragma unroll
@@ -120,8 +101,40 @@ __device__ __forceinline__ void row_moments(const uint8_t* img, const uint8_t* e
   m01 = __reduce_add_sync(0xffffffffu, m01);
 }
 
+// Loads patch row (lane-15) of the keypoint at (x, y) from global memory (linear addressing, bounded by `end`)
+// into w[0..7] and returns the warp's moments.
+__device__ __forceinline__ void row_moments(const uint8_t* img, const uint8_t* end, int vstep, int x, int y,
+                                            const uint32_t* s_wx, const uint32_t* s_w1, uint32_t w[8], int32_t& m10,
+                                            int32_t& m01) {
+  const int lane = threadIdx.x & 31;
+  uint32_t q[13];
+#pragma unroll
+  for (int k = 0; k < 13; ++k) q[k] = 0u;
+  uint32_t ob = 0;
+  if (lane < 31) {
+    const uint8_t* a = img + (size_t)(y + lane - 15) * vstep + (x - 15);
+    const uintptr_t ai = reinterpret_cast<uintptr_t>(a);
+    ob = (uint32_t)(ai & 15);  // byte offset of column x-15 inside its 16-byte chunk
+    const uint8_t* a16 = reinterpret_cast<const uint8_t*>(ai & ~(uintptr_t)15);
+    // three 16-byte loads cover bytes ob .. ob+30 (<= 45): one L1 wavefront per row and load instead of
+    // one per row and 4-byte word
+    if (a16 + 48 <= end) {
+      const uint4* a4 = reinterpret_cast<const uint4*>(a16);
+      const uint4 c0 = __ldg(a4), c1 = __ldg(a4 + 1), c2 = __ldg(a4 + 2);
+      q[0] = c0.x; q[1] = c0.y; q[2] = c0.z; q[3] = c0.w;
+      q[4] = c1.x; q[5] = c1.y; q[6] = c1.z; q[7] = c1.w;
+      q[8] = c2.x; q[9] = c2.y; q[10] = c2.z; q[11] = c2.w;
+    } else {  // the very end of a buffer
+#pragma unroll
+      for (int k = 0; k < 12; ++k) q[k] = load_word_bounded(a16 + 4 * k, end);
+    }
+  }
+  moments_from_chunks(q, ob, s_wx, s_w1, w, m10, m01);
+}
+
 // One descriptor byte per lane: pairs 8*lane .. 8*lane+7 of angle bin `rot` (Brief.h:28-53, 71-631)
 __device__ __forceinline__ uint32_t brief_byte(const uint8_t* patch, const uint32_t* __restrict__ brief, int rot) {
+  // `patch` points at the byte of (dx,dy) = (-15,-15); the table holds offsets for the patch's row pitch
   const int lane = threadIdx.x & 31;
   const uint4* t = reinterpret_cast<const uint4*>(brief + rot * 256 + lane * 8);
   const uint4 ta = __ldg(t), tb = __ldg(t + 1);
@@ -180,6 +193,95 @@ __global__ void __launch_bounds__(ORB_WARPS * 32) orb_kernel(const __grid_consta
     __syncwarp();
     const uint32_t b = brief_byte(reinterpret_cast<const uint8_t*>(patch), P.brief, rot);
     if (lane < 4 * P.words) reinterpret_cast<uint8_t*>(desc)[lane] = (uint8_t)b;
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+// Fused-path descriptor kernel with TMA patch prefetch.  Every warp owns two 31 x 48-byte patch buffers
+// and two mbarriers: lane 0 issues the box load of the NEXT keypoint (box origin = column (x-15) & ~15, a
+// TMA box must start on a 16-byte column) before the warp waits for the CURRENT one, so the L2 latency of
+// a patch hides behind the previous keypoint's arithmetic and no load instruction touches the pixels.
+// The pattern is evaluated straight out of the TMA buffer (table offsets for a 48-byte pitch + ob).
+// --------------------------------------------------------------------------------------------------
+constexpr int OT_W = 48, OT_H = 31, OT_BYTES = OT_W * OT_H, OT_STRIDE = 1536;
+
+struct OrbKp {
+  int frame, i, x, y;
+};
+
+__global__ void __launch_bounds__(ORB_WARPS * 32) orb_tma_kernel(const __grid_constant__ OrbParams P,
+                                                                 const __grid_constant__ CUtensorMap tmap) {
+  __shared__ __align__(128) uint8_t s_buf[ORB_WARPS][2][OT_STRIDE];
+  __shared__ __align__(8) uint64_t s_bar[ORB_WARPS][2];
+  __shared__ uint32_t s_wx[16 * 9], s_w1[16 * 9];
+  build_disc_tables(s_wx, s_w1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    mbar_init(&s_bar[warp][0], 1);
+    mbar_init(&s_bar[warp][1], 1);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const long long nwarps = (long long)gridDim.x * ORB_WARPS;
+  const long long nslots = (long long)P.nframes * P.cap;
+  long long slot = (long long)blockIdx.x * ORB_WARPS + warp - nwarps;
+
+  // next occupied slot of this warp's stride (all lanes compute the same values)
+  auto advance = [&](OrbKp& k) -> bool {
+    for (;;) {
+      slot += nwarps;
+      if (slot >= nslots) return false;
+      const int frame = (int)(slot / P.cap);
+      const int i = (int)(slot - (long long)frame * P.cap);
+      const uint8_t* rec = P.records + (size_t)frame * P.rec.bytes;
+      if (i >= (int)__ldg(reinterpret_cast<const uint32_t*>(rec))) continue;
+      const uint32_t e = __ldg(reinterpret_cast<const uint32_t*>(rec + P.rec.kp_off) + i);
+      k.frame = frame;
+      k.i = i;
+      k.x = (int)decode_x(e);
+      k.y = (int)decode_y(e) + P.row_off[__ldg(rec + P.rec.level_off + i)];
+      return true;
+    }
+  };
+  auto issue = [&](const OrbKp& k, int b) {
+    if (lane == 0) {
+      mbar_expect_tx(&s_bar[warp][b], OT_BYTES);
+      tma_load_3d(s_buf[warp][b], &tmap, (k.x - 15) & ~15, k.y - 15, k.frame, &s_bar[warp][b]);
+    }
+  };
+
+  OrbKp cur, nxt;
+  bool have = advance(cur);
+  if (have) issue(cur, 0);
+  int b = 0;
+  uint32_t phase = 0;  // bit b = parity to wait for on buffer b
+  while (have) {
+    const bool have_next = advance(nxt);
+    if (have_next) issue(nxt, b ^ 1);
+    mbar_wait(&s_bar[warp][b], (phase >> b) & 1u);
+    phase ^= 1u << b;
+
+    const uint8_t* buf = s_buf[warp][b];
+    const uint32_t ob = (uint32_t)((cur.x - 15) & 15);
+    uint32_t q[13];
+    {
+      const uint4* r4 = reinterpret_cast<const uint4*>(buf + (lane < 31 ? lane : 0) * OT_W);
+      const uint4 c0 = r4[0], c1 = r4[1], c2 = r4[2];
+      q[0] = c0.x; q[1] = c0.y; q[2] = c0.z; q[3] = c0.w;
+      q[4] = c1.x; q[5] = c1.y; q[6] = c1.z; q[7] = c1.w;
+      q[8] = c2.x; q[9] = c2.y; q[10] = c2.z; q[11] = c2.w;
+    }
+    uint32_t w[8];
+    int32_t m10, m01;
+    moments_from_chunks(q, ob, s_wx, s_w1, w, m10, m01);
+    const int rot = (int)angle_bin(m10, m01);
+    const uint32_t bits = brief_byte(buf + ob, P.brief48, rot);
+    uint8_t* rec = P.records + (size_t)cur.frame * P.rec.bytes;
+    if (lane < 4 * P.words) (rec + P.rec.desc_off)[((size_t)cur.i * P.words) * 4 + lane] = (uint8_t)bits;
+    __syncwarp();  // every lane is done with buf before lane 0 lets the next TMA overwrite it
+    cur = nxt;
+    have = have_next;
+    b ^= 1;
   }
 }
 

@@ -152,7 +152,8 @@ struct pislam_ctx {
   int num_sms = 148;
   bool use_tma = true;
   EncodeTiledFn encode = nullptr;
-  uint32_t* d_brief = nullptr;
+  uint32_t* d_brief = nullptr;    // pattern offsets for the 36-byte patch pitch
+  uint32_t* d_brief48 = nullptr;  // ... for the 48-byte pitch of the TMA patch buffers
   // literal stages
   DevBuf img, out, kp, desc, aux0, aux1;
   // fused path
@@ -284,10 +285,10 @@ int prepare_geometry(pislam_ctx* c, const pislam_pyramid_desc* d, int cap) {
 }
 
 int make_tensor_map(pislam_ctx* c, CUtensorMap* m, const uint8_t* base, int vstep, long long rows, int nframes,
-                    size_t frame_stride) {
+                    size_t frame_stride, int box_w = PIX_W, int box_h = PIX_H) {
   const cuuint64_t dims[3] = {(cuuint64_t)vstep, (cuuint64_t)rows, (cuuint64_t)nframes};
   const cuuint64_t strides[2] = {(cuuint64_t)vstep, (cuuint64_t)(nframes > 1 ? frame_stride : (size_t)rows * vstep)};
-  const cuuint32_t box[3] = {PIX_W, PIX_H, 1};
+  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -385,12 +386,24 @@ int enqueue_extract(pislam_ctx* c, const uint8_t* d_stacks, size_t frame_stride,
     Q.rec = RecordLayout::make(cap, d->words);
     for (int l = 0; l < d->nlevels; ++l) Q.row_off[l] = d->row_offsets[l];
     Q.brief = c->d_brief;
+    Q.brief48 = c->d_brief48;
     Q.nframes = nframes;
     Q.cap = cap;
     const long long want = ((long long)nframes * cap + ORB_WARPS - 1) / ORB_WARPS;
-    const dim3 grid((unsigned)std::min<long long>(want, (long long)c->num_sms * 8));
+    CUtensorMap omap;
+    memset(&omap, 0, sizeof(omap));
+    // the patch prefetch needs 16-byte-aligned rows and descriptors' border >= 16 keeps every patch column
+    // inside its level row (no wrap into the next row, which a box load would zero-fill instead)
+    const bool orb_tma = tma_ok && d->vstep >= OT_W &&
+                         make_tensor_map(c, &omap, d_stacks, d->vstep, g.rows, nframes, frame_stride, OT_W, OT_H) == PISLAM_OK;
     span_begin(c, 2);
-    orb_kernel<1><<<grid, ORB_WARPS * 32, 0, c->stream>>>(Q);
+    if (orb_tma) {
+      const dim3 grid((unsigned)std::min<long long>(want, (long long)c->num_sms * 8));
+      orb_tma_kernel<<<grid, ORB_WARPS * 32, 0, c->stream>>>(Q, omap);
+    } else {
+      const dim3 grid((unsigned)std::min<long long>(want, (long long)c->num_sms * 8));
+      orb_kernel<1><<<grid, ORB_WARPS * 32, 0, c->stream>>>(Q);
+    }
     span_end(c);
     CKS(check_launch(c));
   }
@@ -488,6 +501,16 @@ int pislam_b200_create(pislam_ctx** out, int device, size_t max_stack_bytes, int
       st = -(int)e;
       break;
     }
+    for (int i = 0; i < 30 * 256; ++i) {
+      const uint32_t o0 = (uint32_t)((t[4 * i + 1] + 15) * OT_W + (t[4 * i + 0] + 15));
+      const uint32_t o1 = (uint32_t)((t[4 * i + 3] + 15) * OT_W + (t[4 * i + 2] + 15));
+      offs[i] = o0 | (o1 << 16);
+    }
+    if ((e = cudaMalloc(&c->d_brief48, offs.size() * 4)) != cudaSuccess) { st = -(int)e; break; }
+    if ((e = cudaMemcpy(c->d_brief48, offs.data(), offs.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+      st = -(int)e;
+      break;
+    }
     if (max_stack_bytes && (e = c->stacks.reserve(max_stack_bytes)) != cudaSuccess) { st = -(int)e; break; }
     (void)max_keypoints;
   } while (0);
@@ -510,6 +533,7 @@ int pislam_b200_destroy(pislam_ctx* c) {
                     &c->piece_cnt, &c->piece_off, &c->stacks, &c->records, &c->hdr};
   for (DevBuf* b : bufs) b->release();
   if (c->d_brief) cudaFree(c->d_brief);
+  if (c->d_brief48) cudaFree(c->d_brief48);
   for (int i = 0; i < pislam_ctx::kMaxChunks; ++i) {
     if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
     if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
