@@ -113,10 +113,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
 // --------------------------------------------------------------------------------------------------
 // SWAR helpers: four pixels per 32-bit word
 // --------------------------------------------------------------------------------------------------
-// bit 7 of every byte: (byte of d) > t, for a uniform t in 0..255; k7 = (0x7f - (t & 0x7f)) * 0x01010101
-__device__ __forceinline__ uint32_t bytes_gt(uint32_t d, uint32_t k7, bool t_lt_128) {
+// bit 7 of every byte: (byte of d) > t, for a uniform t in 0..255; k7 = (0x7f - (t & 0x7f)) * 0x01010101.
+// With s = low 7 bits + k7 (bit 7 of s: low7 > t7): t < 128 needs d | s, t >= 128 needs d & s; `m_or` is
+// all-ones / zero accordingly, so both cases are one three-input logic op.
+__device__ __forceinline__ uint32_t bytes_gt(uint32_t d, uint32_t k7, uint32_t m_or) {
   const uint32_t s = (d & 0x7f7f7f7fu) + k7;
-  return t_lt_128 ? (d | s) : (d & s);
+  return (d & s) | ((d | s) & m_or);
 }
 
 // Warp-aggregated append of one 16-bit item per participating lane to a shared list.
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(NT) front_tile_kernel(const __grid_constant__ 
       if (nlo < nhi) {
         const uint32_t colmask = (0x01010101u << (8 * nlo)) & (0x01010101u >> (8 * (4 - nhi)));
         const uint32_t k7 = (0x7fu - (uint32_t)(t & 0x7f)) * 0x01010101u;
-        const bool t_lt_128 = t < 128;
+        const uint32_t t_lt_128 = t < 128 ? 0xffffffffu : 0u;
         const uint32_t* c = reinterpret_cast<const uint32_t*>(s_pix) + r0 * (PIX_W / 4) + (dxo >> 2) + 1 + wx;
         uint32_t I[A_ROWS + 6];
 #pragma unroll
