@@ -24,7 +24,7 @@ namespace pb {
 
 constexpr int TW = 128;             // tile width  (output pixels)
 constexpr int TH = 32;              // tile height (output pixels)
-constexpr int NT = 256;             // threads per CTA
+constexpr int NT = 128;             // threads per CTA
 constexpr int PIX_W = TW + 32;      // staged pixels: origin (x0-8-dxo, y0-4); a TMA box must start on a
                                     // 16-byte boundary of the row, so dxo = (x0-8) & 15 there, 0 otherwise
 constexpr int PIX_H = TH + 10;
@@ -34,7 +34,6 @@ constexpr int SC_WW = SC_W / 4;     // score-tile words per row
 constexpr int NWORD = SC_WW * SC_H; // FAST work items (4 pixels each)
 constexpr int CELLS_X = TW / 2, CELLS_Y = TH / 2;
 constexpr int NCELL = CELLS_X * CELLS_Y;  // 1024 = 4 per thread
-static_assert(NCELL == 4 * NT, "four cells per thread");
 constexpr int MAX_LEVELS = 16;
 
 enum { MODE_TMA = 0, MODE_LDG = 1, MODE_SCOREMAP = 2 };
@@ -151,7 +150,7 @@ __device__ __forceinline__ bool nms_survives(const uint8_t* q, int pitch) {
 constexpr int A_COLS = SC_WW;                       // 34 word columns
 constexpr int A_ROWS = 5;                           // rows per phase-A thread
 constexpr int A_GROUPS = (SC_H + A_ROWS - 1) / A_ROWS;  // 7
-static_assert(A_COLS * A_GROUPS <= NT, "phase A: one thread per (word column, row group)");
+constexpr int A_TASKS = A_COLS * A_GROUPS;          // 238 (word column, row group) tasks
 static_assert(A_GROUPS * A_ROWS + 6 <= PIX_H + 1, "phase A rows stay inside the staged tile");
 
 template <int MODE>
@@ -159,13 +158,15 @@ __global__ void __launch_bounds__(NT) front_tile_kernel(const __grid_constant__ 
                                                         const __grid_constant__ CUtensorMap tmap) {
   __shared__ __align__(128) uint8_t s_pix[PIX_H * PIX_W];
   __shared__ __align__(16) uint8_t s_score[SC_H * SC_W];
-  __shared__ uint16_t s_listA[SC_H * SC_W];  // FAST candidates (A->B), then non-zero scores (C->D)
-  __shared__ uint16_t s_listB[SC_H * SC_W];  // FAST corners (B->C), then NMS survivors (D->D2)
-  __shared__ __align__(16) uint32_t s_cell[NCELL];
-  __shared__ __align__(16) uint32_t s_cell2[NCELL];
-  __shared__ uint32_t s_bm[NCELL / 32], s_pref[NCELL / 32 + 1];
+  __shared__ __align__(16) uint16_t s_listA[SC_H * SC_W];  // FAST candidates (A->B), then non-zero scores (C->D)
+  __shared__ uint16_t s_listB[SC_H * SC_W];                // FAST corners (B->C), then NMS survivors (D->D2)
+  __shared__ uint32_t s_occ[NCELL / 32], s_bm[NCELL / 32], s_pref[NCELL / 32 + 1];
   __shared__ uint32_t s_nA, s_nB, s_nC, s_nS, s_base;
   __shared__ __align__(8) uint64_t s_bar;
+  // the slot arrays reuse buffers that are dead by then: the pixels after phase C, list A after phase D
+  static_assert(sizeof(s_pix) >= NCELL * 4 && sizeof(s_listA) >= NCELL * 4, "slot arrays alias s_pix / s_listA");
+  uint32_t* const s_cell = reinterpret_cast<uint32_t*>(s_pix);
+  uint32_t* const s_cell2 = reinterpret_cast<uint32_t*>(s_listA);
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -195,10 +196,9 @@ __global__ void __launch_bounds__(NT) front_tile_kernel(const __grid_constant__ 
     s_nC = 0;
     s_nS = 0;
   }
-  if (tid < NCELL / 32) s_bm[tid] = 0u;
-  if (lb > 0) {
-    reinterpret_cast<uint4*>(s_cell)[tid] = make_uint4(0u, 0u, 0u, 0u);
-    reinterpret_cast<uint4*>(s_cell2)[tid] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < NCELL / 32) {
+    s_bm[tid] = 0u;
+    s_occ[tid] = 0u;
   }
 
   if (MODE == MODE_SCOREMAP) {
@@ -244,8 +244,9 @@ __global__ void __launch_bounds__(NT) front_tile_kernel(const __grid_constant__ 
     // |p-c| > t on (N or S) and on (E or W).  One thread owns a word column (4 pixels) and 5 rows:
     // V(q) = |I[q+3]-I[q]| > t serves as the S test of row q and the N test of row q+3.
     const int t = P.fast_t & 0xff;  // Fast.h:58 keeps the low byte
-    if (tid < A_COLS * A_GROUPS) {
-      const int g = tid / A_COLS, wx = tid - g * A_COLS;
+    for (int task = tid; task < ((A_TASKS + 31) & ~31); task += NT) {
+      if (task >= A_TASKS) break;  // whole lanes beyond the last task: the partial warp is handled below
+      const int g = task / A_COLS, wx = task - g * A_COLS;
       const int r0 = g * A_ROWS;
       const int x = x0 - 4 + 4 * wx;
       const int xlo = max(B, x0 - 1), xhi = min(L.xend, x0 + TW + 1);  // columns whose flag matters here
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(NT) front_tile_kernel(const __grid_constant__ 
       }
       // one list reservation per warp for all rows
       // the last warp of phase A is partial (threads 224..237): its highest lane reserves
-      const int last = min(31, A_COLS * A_GROUPS - 1 - (tid & ~31));
+      const int last = min(31, A_TASKS - 1 - (task & ~31));
       const uint32_t amask = 0xffffffffu >> (31 - last);
       const uint32_t cnt = (uint32_t)__popc(acc);
       uint32_t incl = cnt;
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(NT) front_tile_kernel(const __grid_constant__ 
         slot = ((cy >> cb_log) << (6 + cb_log)) + ((cx >> cb_log) << (2 * cb_log)) + ((cy & cbm) << cb_log) + (cx & cbm);
       }
       s_cell[slot] = encode_fast(q[0], x0 - 4 + sx, y0 - 1 + ry);
-      if (lb == 0) atomicOr(&s_bm[slot >> 5], 1u << (slot & 31));
+      atomicOr((lb == 0 ? s_bm : s_occ) + (slot >> 5), 1u << (slot & 31));
     }
     if (lb > 0) warp_push(surv, (uint16_t)slot, s_listB, &s_nS);
   }
@@ -366,14 +367,16 @@ __global__ void __launch_bounds__(NT) front_tile_kernel(const __grid_constant__ 
       const int s = s_listB[i];
       const uint32_t v = s_cell[s];
       const int b0 = s & ~(bslots - 1);
-      int cnt = 1, rank = 0;
-      if (bslots >= 4) {
-        cnt = 0;
-        const uint4* b4 = reinterpret_cast<const uint4*>(s_cell + b0);
-        for (int k = 0; k < (bslots >> 2); ++k) {
-          const uint4 o = b4[k];
-          cnt += (o.x != 0u) + (o.y != 0u) + (o.z != 0u) + (o.w != 0u);
-          rank += (o.x > v) + (o.y > v) + (o.z > v) + (o.w > v);
+      // the bucket's occupied slots: cnt of them, rank = how many hold a larger encoded value
+      int cnt = 0, rank = 0;
+      const uint32_t wmask = bslots >= 32 ? 0xffffffffu : (((1u << bslots) - 1u) << (b0 & 31));
+      for (int wd = b0 >> 5; wd <= (b0 + bslots - 1) >> 5; ++wd) {
+        uint32_t bits = s_occ[wd] & wmask;
+        cnt += __popc(bits);
+        while (bits) {
+          const int j = __ffs(bits) - 1;
+          bits &= bits - 1;
+          rank += s_cell[(wd << 5) + j] > v;
         }
       }
       const int kept = min(cnt, P.bucket_limit);
@@ -402,14 +405,14 @@ __global__ void __launch_bounds__(NT) front_tile_kernel(const __grid_constant__ 
   }
   __syncthreads();
   const uint32_t base = s_base;
-  {
-    const uint32_t w = s_bm[tid >> 3];
-    const int sh = (tid & 7) * 4;
-    uint32_t nib = (w >> sh) & 15u;
+  for (int g = tid; g < NCELL / 4; g += NT) {  // slots 4g .. 4g+3
+    const uint32_t w = s_bm[g >> 3];
+    const int sh = (g & 7) * 4;
+    const uint32_t nib = (w >> sh) & 15u;
     if (nib) {
       uint32_t* stage = P.stage + (size_t)frame * P.cap;
-      uint32_t pos = base + s_pref[tid >> 3] + (uint32_t)__popc(w & ((1u << sh) - 1u));
-      const uint4 v = reinterpret_cast<const uint4*>(cells)[tid];
+      uint32_t pos = base + s_pref[g >> 3] + (uint32_t)__popc(w & ((1u << sh) - 1u));
+      const uint4 v = reinterpret_cast<const uint4*>(cells)[g];
       const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j)
