@@ -143,8 +143,15 @@ __device__ __forceinline__ uint32_t dp4a_uu(uint32_t pix, uint32_t w_u8, uint32_
   return r;
 }
 
-// ARM FPRecipEstimate (vrecpeq_f32, Orb.h:329): 8 fractional bits, flush-to-zero.
-__device__ __forceinline__ float recpe(float x) {
+// ARM FPRecipEstimate (vrecpeq_f32, Orb.h:329): 8 fractional bits, flush-to-zero.  The estimate depends on the
+// top 8 fraction bits only: q = 256 + (frac >> 15), s = floor(2^19 / (2q+1) + 1/2) in [256, 511].
+__device__ __forceinline__ uint32_t recpe_mantissa(uint32_t top8) {
+  const uint32_t q2 = 2u * (256u + top8) + 1u;  // 2q+1
+  return (524288u + q2) / (2u * q2);            // floor(2^18/(2q+1) + 1/2)
+}
+
+// `lut`, when given, holds recpe_mantissa(0..255) (built once per CTA: the division is ~20 instructions)
+__device__ __forceinline__ float recpe(float x, const uint16_t* lut = nullptr) {
   const uint32_t u = __float_as_uint(x);
   const uint32_t sign = u & 0x80000000u, e = (u >> 23) & 0xffu, frac = u & 0x7fffffu;
   uint32_t o;
@@ -152,18 +159,17 @@ __device__ __forceinline__ float recpe(float x) {
   else if (e == 0) o = sign | 0x7f800000u;
   else if (e >= 253) o = sign;
   else {
-    const uint32_t q2 = 2u * (256u + (frac >> 15)) + 1u;  // 2q+1, q = floor(scaled*512)
-    const uint32_t s = (524288u + q2) / (2u * q2);         // floor(2^18/(2q+1) + 1/2)
+    const uint32_t s = lut ? (uint32_t)lut[frac >> 15] : recpe_mantissa(frac >> 15);
     o = sign | ((253u - e) << 23) | ((s - 256u) << 15);
   }
   return __uint_as_float(o);
 }
 
 // Every fp32 operation individually rounded (no FMA contraction): Orb.h:338-350.
-__device__ __forceinline__ uint32_t angle_bin(int32_t m10, int32_t m01) {
+__device__ __forceinline__ uint32_t angle_bin(int32_t m10, int32_t m01, const uint16_t* recpe_lut = nullptr) {
   const float ax = fabsf(__int2float_rn(m10)), ay = fabsf(__int2float_rn(m01));
   const float zmax = fmaxf(ax, ay), zmin = fminf(ax, ay);
-  const float z = __fmul_rn(zmin, recpe(zmax));  // flat patch: 0 * inf = NaN
+  const float z = __fmul_rn(zmin, recpe(zmax, recpe_lut));  // flat patch: 0 * inf = NaN
   const float c0 = (float)(256 * 14.999998), c1 = (float)(256 * 4.723436), c2 = (float)(256 * 1.266240);
   const float t1 = __fadd_rn(c1, __fmul_rn(c2, z));
   const float t3 = __fmul_rn(__fsub_rn(z, 1.0f), t1);

@@ -214,7 +214,9 @@ __global__ void __launch_bounds__(ORB_WARPS * 32) orb_tma_kernel(const __grid_co
   __shared__ __align__(128) uint8_t s_buf[ORB_WARPS][2][OT_STRIDE];
   __shared__ __align__(8) uint64_t s_bar[ORB_WARPS][2];
   __shared__ uint32_t s_wx[16 * 9], s_w1[16 * 9];
+  __shared__ uint16_t s_recpe[256];
   build_disc_tables(s_wx, s_w1);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_recpe[i] = (uint16_t)recpe_mantissa((uint32_t)i);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) {
     mbar_init(&s_bar[warp][0], 1);
@@ -222,24 +224,34 @@ __global__ void __launch_bounds__(ORB_WARPS * 32) orb_tma_kernel(const __grid_co
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  const long long nwarps = (long long)gridDim.x * ORB_WARPS;
-  const long long nslots = (long long)P.nframes * P.cap;
-  long long slot = (long long)blockIdx.x * ORB_WARPS + warp - nwarps;
+  // this warp visits slots gw, gw + nwarps, ... of the (frame, slot-in-record) space; the position is kept
+  // as (frame, i) and advanced by (nwarps / cap, nwarps % cap) so that no division sits in the loop
+  const int nwarps = (int)gridDim.x * ORB_WARPS;
+  const int dq = nwarps / P.cap, dr = nwarps % P.cap;
+  const int gw = (int)blockIdx.x * ORB_WARPS + warp;
+  int frame = gw / P.cap - dq, idx = gw % P.cap - dr;
+  if (idx < 0) {
+    idx += P.cap;
+    --frame;
+  }
 
   // next occupied slot of this warp's stride (all lanes compute the same values)
   auto advance = [&](OrbKp& k) -> bool {
     for (;;) {
-      slot += nwarps;
-      if (slot >= nslots) return false;
-      const int frame = (int)(slot / P.cap);
-      const int i = (int)(slot - (long long)frame * P.cap);
+      frame += dq;
+      idx += dr;
+      if (idx >= P.cap) {
+        idx -= P.cap;
+        ++frame;
+      }
+      if (frame >= P.nframes) return false;
       const uint8_t* rec = P.records + (size_t)frame * P.rec.bytes;
-      if (i >= (int)__ldg(reinterpret_cast<const uint32_t*>(rec))) continue;
-      const uint32_t e = __ldg(reinterpret_cast<const uint32_t*>(rec + P.rec.kp_off) + i);
+      if (idx >= (int)__ldg(reinterpret_cast<const uint32_t*>(rec))) continue;
+      const uint32_t e = __ldg(reinterpret_cast<const uint32_t*>(rec + P.rec.kp_off) + idx);
       k.frame = frame;
-      k.i = i;
+      k.i = idx;
       k.x = (int)decode_x(e);
-      k.y = (int)decode_y(e) + P.row_off[__ldg(rec + P.rec.level_off + i)];
+      k.y = (int)decode_y(e) + P.row_off[__ldg(rec + P.rec.level_off + idx)];
       return true;
     }
   };
@@ -274,10 +286,10 @@ __global__ void __launch_bounds__(ORB_WARPS * 32) orb_tma_kernel(const __grid_co
     uint32_t w[8];
     int32_t m10, m01;
     moments_from_chunks(q, ob, s_wx, s_w1, w, m10, m01);
-    const int rot = (int)angle_bin(m10, m01);
+    const int rot = (int)angle_bin(m10, m01, s_recpe);
     const uint32_t bits = brief_byte(buf + ob, P.brief48, rot);
     uint8_t* rec = P.records + (size_t)cur.frame * P.rec.bytes;
-    if (lane < 4 * P.words) (rec + P.rec.desc_off)[((size_t)cur.i * P.words) * 4 + lane] = (uint8_t)bits;
+    if (lane < 4 * P.words) (rec + P.rec.desc_off)[(uint32_t)(cur.i * P.words * 4 + lane)] = (uint8_t)bits;
     __syncwarp();  // every lane is done with buf before lane 0 lets the next TMA overwrite it
     cur = nxt;
     have = have_next;
