@@ -131,7 +131,15 @@ def run_reference_arm(args):
         "e2e": {"value": mpix, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+def emit(line):
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
+
+
+_OUT = sys.stdout
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -190,6 +198,7 @@ def run_gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     F = args.frames
@@ -204,8 +213,11 @@ def run_gpu_arm(args):
     h_stacks.numpy()[:] = frames
     h_records = torch.empty(F * rec_bytes, dtype=torch.uint8, pin_memory=True)
     d_stacks = h_stacks.to("cuda", non_blocking=False)
-    d_all = torch.zeros(world * F * rec_bytes, dtype=torch.uint8, device="cuda")
+    # two gather buffers: the all-gather of step k runs under the kernels of step k+1
+    d_alls = [torch.zeros(world * F * rec_bytes, dtype=torch.uint8, device="cuda") for _ in range(2 if world > 1 else 1)]
+    d_all = d_alls[0]
     d_records = d_all[rank * F * rec_bytes:(rank + 1) * F * rec_bytes]
+    turn = [0]
 
     ctx = api.Context(local)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
@@ -222,7 +234,9 @@ def run_gpu_arm(args):
     def step_device():
         """inputs resident in HBM; results (this rank's records, all-gathered when N>1) left in HBM"""
         if world > 1 and gather.startswith("ncclAllGather"):
-            st = ctx.extract_allgather_ptr(d_stacks.data_ptr(), frame_bytes, F, desc, CAP, d_all.data_ptr())
+            buf = d_alls[turn[0]]
+            turn[0] ^= 1
+            st = ctx.extract_allgather_ptr(d_stacks.data_ptr(), frame_bytes, F, desc, CAP, buf.data_ptr())
         else:
             st = ctx.extract_batch_ptr(d_stacks.data_ptr(), frame_bytes, F, desc, CAP, d_records.data_ptr(),
                                        asynchronous=True)
@@ -233,14 +247,24 @@ def run_gpu_arm(args):
             raise RuntimeError("extract failed: %d" % st)
 
     def step_e2e():
-        """the call a user makes: HOST stacks in, HOST records out (H2D + kernels + D2H inside)"""
-        st = ctx.extract_batch_ptr(h_stacks.data_ptr(), frame_bytes, F, desc, CAP, h_records.data_ptr())
+        """the call a user makes: HOST stacks in, HOST records out (H2D + kernels + D2H inside); with N > 1 the
+        records are extracted into this rank's slot of the device gather buffer, all-gathered over NVLink, and the
+        rank's own records are read back to the host"""
+        if world == 1:
+            st = ctx.extract_batch_ptr(h_stacks.data_ptr(), frame_bytes, F, desc, CAP, h_records.data_ptr())
+        else:
+            st = ctx.extract_batch_ptr(h_stacks.data_ptr(), frame_bytes, F, desc, CAP, d_records.data_ptr())
+            if st in (0, api.PISLAM_ERR_CAPACITY):
+                if gather.startswith("ncclAllGather"):
+                    g = ctx.allgather_ptr(d_all.data_ptr(), F * rec_bytes)
+                    if g != 0:
+                        raise RuntimeError("allgather failed: %d" % g)
+                with torch.cuda.stream(stream):
+                    if not gather.startswith("ncclAllGather"):
+                        dist.all_gather_into_tensor(d_all, d_records)
+                    h_records.copy_(d_records, non_blocking=True)
         if st not in (0, api.PISLAM_ERR_CAPACITY):
             raise RuntimeError("extract failed: %d" % st)
-        if world > 1:
-            with torch.cuda.stream(stream):
-                d_records.copy_(h_records, non_blocking=True)
-                dist.all_gather_into_tensor(d_all, d_records)
 
     def barrier():
         if world > 1:
@@ -257,6 +281,7 @@ def run_gpu_arm(args):
         e0.record(stream)
         for _ in range(steps):
             fn()
+        ctx.join()  # the last all-gather (second stream) belongs to the timed region
         e1.record(stream)
         barrier()
         t1 = time.perf_counter()
@@ -313,8 +338,9 @@ def run_gpu_arm(args):
                        "stack_bytes_per_frame": frame_bytes, "keypoints_per_frame": kpts_total / (F * world),
                        "l2_policy": "inputs larger than L2 (%d MB of stacks per GPU per step)" % (F * frame_bytes >> 20),
                        "cap": CAP, "capacity_overflows": overflow, "gather": gather,
-                       "parallelism": "frames sharded one batch per GPU, one all-gather of records" if world > 1
-                       else "single GPU"},
+                       "parallelism": "frames sharded one batch per GPU, one all-gather of records per step "
+                                      "(overlapping the next step's kernels)" if world > 1 else "single GPU",
+                       "numa_node_rank0": numa},
             "keypoints_per_s": kpts_total * args.steps / (ms_dev * 1e-3),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": F * VGA.level_pixels,
                     "h2d_note": "level pixels only: the padding right of each level is not uploaded",
@@ -327,13 +353,13 @@ def run_gpu_arm(args):
                              "kind": cpu.kind, "keypoints_per_s": ck / dt,
                              "sample": "%d frames once on %d host threads, one pyramid per task" % (nf, cores)},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     # teardown order matters: torch may still hold blocks it used on the ctx stream (an ExternalStream);
     # release them before the stream is destroyed with the context
     if world > 1:
         dist.barrier()
     barrier()
-    del d_records, d_all, d_stacks, h_stacks, h_records, stream
+    del d_records, d_all, d_alls, d_stacks, h_stacks, h_records, stream
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
     if world > 1:
@@ -362,14 +388,50 @@ def kernel_roofline(ctx, api, d_stacks, frame_bytes, F, desc, d_records, kpts, s
     t_front = ms[0] / cnt[0] * 1e-3
     alg_bytes = VGA.level_pixels * F + 4 * kpts
     achieved = alg_bytes / t_front / 1e9
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes of one launch from the committed ncu --set full capture (same workload and batch size)
+        with open(os.path.join(ROOT, "profiles", "front_kernel_traffic.json")) as f:
+            tr = json.load(f)
+        if tr["frames_per_launch"] == F:
+            traffic, traffic_src = tr["dram_bytes_read"] + tr["dram_bytes_write"], tr["source"]
+    except Exception:  # noqa: BLE001
+        pass
     return {"kernel": "front_tile_kernel<TMA>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": t_front * 1e3,
             "launches_timed": int(cnt[0]),
             "other_kernels_avg_ms": {"order_kernel": ms[1] / max(cnt[1], 1), "orb_kernel": ms[2] / max(cnt[2], 1)}}
 
 
+def bind_to_gpu_numa(local_rank):
+    """Pin this process (and so its first-touch pinned buffers) to the CPUs of the GPU's NUMA node."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def main():
+    # the contract is ONE JSON line on stdout: libraries that chat on fd 1 (NCCL prints its version there) are
+    # sent to stderr, and the line goes to the saved descriptor
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -145,12 +145,21 @@ int pislam_b200_comm_unique_id(void* id128);
 int pislam_b200_comm_init(pislam_ctx* ctx, int nranks, int rank, const void* id128);
 int pislam_b200_comm_destroy(pislam_ctx* ctx);
 /* extract_batch on this rank's `nframes_local` frames, then a single ncclAllGather of the
- * fixed-capacity records on the same stream: d_all_records (device) receives
- * nranks * nframes_local * record_bytes, rank-major.  Stream-ordered; call
- * pislam_b200_synchronize to wait. */
+ * fixed-capacity records: d_all_records (device) receives nranks * nframes_local * record_bytes,
+ * rank-major; the kernels write this rank's records straight into its slot (in-place gather).
+ * The gather is issued on a second stream behind the kernels, so with two alternating gather
+ * buffers it overlaps the next batch's kernels; a buffer is never rewritten before its previous
+ * gather has finished.  Enqueue only: pislam_b200_synchronize waits for kernels and gathers. */
 int pislam_b200_extract_allgather(pislam_ctx* ctx, const uint8_t* d_stacks, size_t frame_stride,
                                   int nframes_local, const pislam_pyramid_desc* desc, int cap,
                                   void* d_all_records);
+
+/* Makes the ctx stream wait (on the device) for the gathers issued so far by pislam_b200_extract_allgather,
+ * so that later work -- or an event recorded -- on the ctx stream is ordered after them. */
+int pislam_b200_join(pislam_ctx* ctx);
+/* In-place ncclAllGather on the ctx stream of a rank-major buffer whose slot `rank` (bytes_per_rank
+ * bytes) this rank has already filled, e.g. with pislam_b200_extract_batch on device records. */
+int pislam_b200_allgather(pislam_ctx* ctx, void* d_all, size_t bytes_per_rank);
 
 /* ---- introspection for tests ----------------------------------------------------------------- */
 /* The rotated + clamped rBRIEF pattern the device uses, int8[30][256][4] = (x0,y0,x1,y1)

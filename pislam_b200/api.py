@@ -82,6 +82,8 @@ _SIGNATURES = {
     "pislam_b200_comm_destroy": (C.c_int, [C.c_void_p]),
     "pislam_b200_extract_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
                                                 C.POINTER(PyramidDesc), C.c_int, C.c_void_p]),
+    "pislam_b200_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "pislam_b200_join": (C.c_int, [C.c_void_p]),
     "pislam_b200_brief_table": (C.c_int, [C.POINTER(C.c_int8)]),
 }
 
@@ -333,6 +335,12 @@ class Context:
 
     def comm_destroy(self):
         self._ok(self.lib.pislam_b200_comm_destroy(self._h))
+
+    def join(self):
+        self._ok(self.lib.pislam_b200_join(self._h))
+
+    def allgather_ptr(self, all_ptr, bytes_per_rank):
+        return self.lib.pislam_b200_allgather(self._h, all_ptr, bytes_per_rank)
 
     def extract_allgather_ptr(self, stacks_ptr, frame_stride, nframes_local, desc, cap, all_records_ptr):
         return self.lib.pislam_b200_extract_allgather(self._h, stacks_ptr, frame_stride, nframes_local,

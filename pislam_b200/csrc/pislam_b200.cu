@@ -159,9 +159,16 @@ struct pislam_ctx {
   // fused path
   Geometry geo;
   DevBuf tiles, stage, stage_count, piece_cnt, piece_off, stacks, records, hdr;
-  // multi-GPU
+  // multi-GPU: the all-gather runs on its own stream so that it overlaps the next batch's kernels
   NcclComm comm = nullptr;
   int nranks = 1, rank = 0;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_extract = nullptr;
+  struct GatherSlot {
+    void* ptr = nullptr;  // gather buffer last used with this event
+    cudaEvent_t done = nullptr;
+  } gathers[2];
+  int gather_turn = 0;
   // host-buffer batches are pipelined in chunks: H2D (copy_in) | kernels (stream) | D2H (copy_out)
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   static const int kMaxChunks = 8;
@@ -471,6 +478,11 @@ int pislam_b200_create(pislam_ctx** out, int device, size_t max_stack_bytes, int
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { st = -(int)e; break; }
     if ((e = cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking)) != cudaSuccess) { st = -(int)e; break; }
     if ((e = cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking)) != cudaSuccess) { st = -(int)e; break; }
+    if ((e = cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking)) != cudaSuccess) { st = -(int)e; break; }
+    if ((e = cudaEventCreateWithFlags(&c->ev_extract, cudaEventDisableTiming)) != cudaSuccess) { st = -(int)e; break; }
+    for (int i = 0; i < 2 && st == PISLAM_OK; ++i)
+      if ((e = cudaEventCreateWithFlags(&c->gathers[i].done, cudaEventDisableTiming)) != cudaSuccess) st = -(int)e;
+    if (st != PISLAM_OK) break;
     for (int i = 0; i < pislam_ctx::kMaxChunks && st == PISLAM_OK; ++i) {
       if ((e = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming)) != cudaSuccess) st = -(int)e;
       else if ((e = cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming)) != cudaSuccess) st = -(int)e;
@@ -528,6 +540,7 @@ int pislam_b200_destroy(pislam_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->copy_in) cudaStreamSynchronize(c->copy_in);
   if (c->copy_out) cudaStreamSynchronize(c->copy_out);
+  if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   DevBuf* bufs[] = {&c->img, &c->out, &c->kp, &c->desc, &c->aux0, &c->aux1, &c->tiles, &c->stage, &c->stage_count,
                     &c->piece_cnt, &c->piece_off, &c->stacks, &c->records, &c->hdr};
@@ -538,6 +551,10 @@ int pislam_b200_destroy(pislam_ctx* c) {
     if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
     if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
   }
+  if (c->ev_extract) cudaEventDestroy(c->ev_extract);
+  for (int i = 0; i < 2; ++i)
+    if (c->gathers[i].done) cudaEventDestroy(c->gathers[i].done);
+  if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->copy_in) cudaStreamDestroy(c->copy_in);
   if (c->copy_out) cudaStreamDestroy(c->copy_out);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -564,6 +581,7 @@ void* pislam_b200_stream(pislam_ctx* c) { return c ? (void*)c->stream : nullptr;
 int pislam_b200_synchronize(pislam_ctx* c) {
   if (!c) return PISLAM_ERR_INVALID_ARG;
   CK(cudaStreamSynchronize(c->stream));
+  CK(cudaStreamSynchronize(c->comm_stream));
   return PISLAM_OK;
 }
 
@@ -948,6 +966,7 @@ int pislam_b200_comm_destroy(pislam_ctx* c) {
   if (c->comm) {
     CKS(set_device(c));
     cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->comm_stream);
     g_nccl.CommDestroy(c->comm);
     c->comm = nullptr;
   }
@@ -965,8 +984,36 @@ int pislam_b200_extract_allgather(pislam_ctx* c, const uint8_t* d_stacks, size_t
   const size_t slot = rec_bytes * (size_t)nframes_local;
   // the kernels write this rank's records straight into its slot of the gather buffer (in-place gather)
   uint8_t* mine = static_cast<uint8_t*>(d_all_records) + slot * (size_t)c->rank;
+  // a gather that is still filling this buffer must finish before the kernels write into it again; with two
+  // alternating buffers the previous gather (other buffer) keeps running under this batch's kernels
+  for (int i = 0; i < 2; ++i)
+    if (c->gathers[i].ptr == d_all_records) CK(cudaStreamWaitEvent(c->stream, c->gathers[i].done, 0));
   CKS(enqueue_extract(c, d_stacks, frame_stride, nframes_local, d, cap, mine));
-  const int r = g_nccl.AllGather(mine, d_all_records, slot, /*ncclInt8*/ 0, c->comm, c->stream);
+  CK(cudaEventRecord(c->ev_extract, c->stream));
+  CK(cudaStreamWaitEvent(c->comm_stream, c->ev_extract, 0));
+  const int r = g_nccl.AllGather(mine, d_all_records, slot, /*ncclInt8*/ 0, c->comm, c->comm_stream);
+  if (r != 0) return PISLAM_ERR_NCCL - r;
+  pislam_ctx::GatherSlot& g = c->gathers[c->gather_turn];
+  c->gather_turn ^= 1;
+  g.ptr = d_all_records;
+  CK(cudaEventRecord(g.done, c->comm_stream));
+  return PISLAM_OK;
+}
+
+int pislam_b200_join(pislam_ctx* c) {
+  if (!c) return PISLAM_ERR_INVALID_ARG;
+  CKS(set_device(c));
+  for (int i = 0; i < 2; ++i)
+    if (c->gathers[i].ptr) CK(cudaStreamWaitEvent(c->stream, c->gathers[i].done, 0));
+  return PISLAM_OK;
+}
+
+int pislam_b200_allgather(pislam_ctx* c, void* d_all, size_t bytes_per_rank) {
+  if (!c || !d_all) return PISLAM_ERR_INVALID_ARG;
+  if (!c->comm) return PISLAM_ERR_NCCL;
+  CKS(set_device(c));
+  const uint8_t* mine = static_cast<const uint8_t*>(d_all) + bytes_per_rank * (size_t)c->rank;
+  const int r = g_nccl.AllGather(mine, d_all, bytes_per_rank, /*ncclInt8*/ 0, c->comm, c->stream);
   if (r != 0) return PISLAM_ERR_NCCL - r;
   return PISLAM_OK;
 }
