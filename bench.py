@@ -310,8 +310,10 @@ def run_gpu_arm(args):
 
     # roofline of the dominant kernel: per-kernel CUDA events (library profiling mode), same inputs
     roof = None
+    latency = None
     if rank == 0:
         roof = kernel_roofline(ctx, api, d_stacks, frame_bytes, F, desc, d_records, kpts_local, args.steps)
+        latency = single_frame_latency(ctx, frames[0], desc)
 
     if world > 1:
         t = torch.tensor([kpts_local, overflow], device="cuda", dtype=torch.int64)
@@ -347,6 +349,7 @@ def run_gpu_arm(args):
                     "d2h_bytes_per_step": F * rec_bytes, "ms_per_step": ms_e2e / args.steps,
                     "keypoints_per_s": kpts_total * args.steps / (ms_e2e * 1e-3)},
             "gpu_launches": launches,
+            "single_frame_latency_us": latency,
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": {"value": VGA.level_pixels * nf / dt / 1e6, "unit": UNIT, "cores": cores,
@@ -369,6 +372,18 @@ def run_gpu_arm(args):
             pass
         dist.destroy_process_group()
     ctx.close()
+
+
+def single_frame_latency(ctx, stack, desc, iters=200):
+    """One pyramid at a time through pislam_b200_extract_pyramid (host stack in, host keypoints + descriptors
+    out, blocking): the latency a per-frame caller such as the reference demo loop sees.  Wall clock, mean."""
+    stack = np.ascontiguousarray(stack)
+    for _ in range(10):
+        ctx.extract_pyramid(stack, desc, cap=CAP)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        ctx.extract_pyramid(stack, desc, cap=CAP)
+    return (time.perf_counter() - t0) / iters * 1e6
 
 
 def kernel_roofline(ctx, api, d_stacks, frame_bytes, F, desc, d_records, kpts, steps):

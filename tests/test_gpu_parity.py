@@ -279,3 +279,56 @@ def test_argument_errors(ctx):
     assert e.value.status == api.PISLAM_ERR_INVALID_ARG
     kp, lv, desc = ctx.extract_pyramid(stack, api.make_desc(VGA), cap=64)  # empty image: no keypoints
     assert len(kp) == 0
+
+
+# ------------------------------------------------------------------------------------------ full-size properties
+def test_full_batch_properties(ctx, oracle):
+    """BASELINE-size batch (256 VGA pyramids, buckets <4,3>): size-independent properties instead of 256 oracle runs.
+    (1) a frame's record does not depend on its position in the batch or on its neighbours (every copy of a
+    frame is identical, and equals the frame extracted alone); (2) keypoints are level-sorted and inside the
+    cell-covered area; (3) 16 sampled frames are bit-exact against the oracle; (4) a second run is identical."""
+    nf, ndistinct = 256, 16
+    base = [synthetic_stack(VGA, 40 + i) for i in range(ndistinct)]
+    stacks = np.stack([base[i % ndistinct] for i in range(nf)])
+    d = api.make_desc(VGA, log_bucket=4, bucket_limit=3)
+    res = ctx.extract_batch(stacks, d, cap=2048)
+    res2 = ctx.extract_batch(stacks, d, cap=2048)
+    for f in range(nf):
+        kp, lv, desc, level_start, n_total = res[f]
+        kp0, lv0, desc0, _, _ = res[f % ndistinct]
+        assert n_total == len(kp)
+        assert np.array_equal(kp, kp0) and np.array_equal(lv, lv0) and np.array_equal(desc, desc0), f
+        assert np.array_equal(kp, res2[f][0]) and np.array_equal(desc, res2[f][2]), f
+        assert (np.diff(lv.astype(np.int32)) >= 0).all()
+        x, y = (kp >> 12) & 0xFFF, kp & 0xFFF
+        w = np.asarray(VGA.widths)[lv]
+        h = np.asarray(VGA.heights)[lv]
+        assert (x >= 16).all() and (x <= w - 16).all() and (y >= 16).all() and (y <= h - 16).all()
+        assert ((kp >> 24) > 0).all()
+    for f in range(ndistinct):
+        okp, olv, odesc = oracle_pyramid(oracle, base[f], VGA, log_bucket=4, bucket_limit=3)
+        assert_same(res[f][0], okp, "frame %d keypoints" % f)
+        assert_same(res[f][2], odesc, "frame %d descriptors" % f)
+        alone = ctx.extract_pyramid(base[f], d, cap=2048)
+        assert_same(alone[0], okp, "frame %d alone" % f)
+
+
+def test_shifted_image_shifts_keypoints(ctx):
+    """Translating the image by a multiple of the cell size translates the interior keypoints: detection,
+    scoring and NMS are position-independent (SURVEY spec F3)."""
+    lay = pyramid_layout(640, 480, nlevels=1)
+    a = synthetic_stack(lay, 77)
+    b = np.zeros_like(a)
+    dx, dy = 6, 4
+    b[dy:, dx:] = a[:-dy, :-dx]
+    d = api.make_desc(lay, words=8)
+    ka, _, da = ctx.extract_pyramid(a, d, cap=1 << 14)
+    kb, _, db = ctx.extract_pyramid(b, d, cap=1 << 14)
+    # compare keypoints well inside both images (3x3 NMS + patch radius away from the moved border)
+    def inside(k, ox, oy):
+        x, y = ((k >> 12) & 0xFFF).astype(int) - ox, (k & 0xFFF).astype(int) - oy
+        return (x >= 40) & (x < 560) & (y >= 40) & (y < 400)
+    sa = {(int(k >> 24), int((k >> 12) & 0xFFF), int(k & 0xFFF)): tuple(v) for k, v in zip(ka[inside(ka, 0, 0)], da[inside(ka, 0, 0)])}
+    sb = {(int(k >> 24), int((k >> 12) & 0xFFF) - dx, int(k & 0xFFF) - dy): tuple(v)
+          for k, v in zip(kb[inside(kb, dx, dy)], db[inside(kb, dx, dy)])}
+    assert len(sa) > 50 and sa == sb
