@@ -476,6 +476,7 @@ __global__ void __launch_bounds__(ORDER_NT) order_kernel(const __grid_constant__
   uint8_t* lvl = rec + P.rec.level_off;
   const uint32_t cap = (uint32_t)P.cap;
   if (tid == 0) s_running = 0;
+  if (tid < REC_HEADER_WORDS) header[tid] = 0u;  // unused header words are defined (zero)
   __syncthreads();
   for (int base = 0; base < P.npieces; base += ORDER_NT) {
     const int p = base + tid;
