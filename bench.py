@@ -28,13 +28,21 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-from pislam_b200.pyramid import VGA, synthetic_stack  # noqa: E402
+from pislam_b200 import pyramid as _pyr  # noqa: E402
+from pislam_b200.pyramid import synthetic_stack  # noqa: E402
+
+VGA = _pyr.VGA  # rebound by --layout (the headline metric is quoted on VGA: BASELINE.json configs[1])
 
 METRIC = "orb_frontend_vga_pyramid_throughput"
 UNIT = "Mpix/s"
 WORKLOAD = "VGA 8-level 1.2x stacked pyramid (2210x640), FAST 20 + Harris 2^15 + NMS buckets<4,3> + rBRIEF-256"
 BORDER, FAST_T, HARRIS_T, LOG_BUCKET, BUCKET_LIMIT, WORDS, CAP = 16, 20, 1 << 15, 4, 3, 8, 2048
+LAYOUTS = {"vga": ("VGA", 2048), "fhd": ("FHD", 4096), "uhd": ("UHD", 8192)}  # record capacity: SURVEY.md 8e
 N_DISTINCT = 32  # distinct synthetic frames; the batch cycles through them (each copy is its own memory)
+
+
+def n_distinct():
+    return N_DISTINCT if VGA is _pyr.VGA else 4  # large frames take seconds each to synthesise
 
 
 def measured_peak_gbs():
@@ -46,7 +54,7 @@ def measured_peak_gbs():
 
 
 def make_frames(n):
-    base = [synthetic_stack(VGA, i) for i in range(min(n, N_DISTINCT))]
+    base = [synthetic_stack(VGA, i) for i in range(min(n, n_distinct()))]
     return np.stack([base[i % len(base)] for i in range(n)])
 
 
@@ -66,18 +74,18 @@ class CpuReference:
         self.kind = "reference" if self.ref is not None else "port"
 
     def _ref_frame(self, stack):
+        """The caller loop of demo/demo.cpp:77-101.  orbCompute runs per level on level-local keypoints (same
+        descriptors as one call on stack coordinates, and valid for stacks taller than the 12-bit y range)."""
         ref = self.ref
         out = np.zeros_like(stack)
         n = 0
-        kps = []
         for w, h, r in zip(VGA.widths, VGA.heights, VGA.row_offsets):
             ref.fast_detect(stack, out, BORDER, w, h, FAST_T, row0=r)
             ref.fast_score_harris(stack, out, BORDER, w, h, HARRIS_T, row0=r)
             kp = ref.fast_extract(out, BORDER, w, h, LOG_BUCKET, BUCKET_LIMIT, row0=r, cap=CAP * 4)
-            kps.append((kp & 0xFFFFF000) | ((kp & 0xFFF) + np.uint32(r)))  # demo.cpp:91-97
-        kp = np.concatenate(kps)
-        ref.orb_compute(stack, kp, WORDS)
-        return len(kp)
+            ref.orb_compute(stack[r:], kp, WORDS)
+            n += len(kp)
+        return n
 
     def run(self, stacks, nthreads):
         """Processes every frame once on `nthreads` host threads; returns (seconds, total keypoints)."""
@@ -407,7 +415,7 @@ def kernel_roofline(ctx, api, d_stacks, frame_bytes, F, desc, d_records, kpts, s
     try:  # DRAM bytes of one launch from the committed ncu --set full capture (same workload and batch size)
         with open(os.path.join(ROOT, "profiles", "front_kernel_traffic.json")) as f:
             tr = json.load(f)
-        if tr["frames_per_launch"] == F:
+        if tr["frames_per_launch"] == F and VGA is _pyr.VGA:
             traffic, traffic_src = tr["dram_bytes_read"] + tr["dram_bytes_write"], tr["source"]
     except Exception:  # noqa: BLE001
         pass
@@ -453,7 +461,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=256, help="stacked pyramids per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layout", default="vga", choices=sorted(LAYOUTS),
+                    help="pyramid geometry (default vga = the headline config; fhd/uhd = BASELINE configs 3 and 5)")
     args = ap.parse_args()
+    global VGA, CAP, WORKLOAD
+    name, CAP = LAYOUTS[args.layout]
+    VGA = getattr(_pyr, name)
+    if args.layout != "vga":
+        WORKLOAD = "%s 8-level 1.2x stacked pyramid (%dx%d), FAST 20 + Harris 2^15 + NMS buckets<4,3> + rBRIEF-256" % (
+            name, VGA.rows, VGA.vstep)
     if args.impl == "reference":
         run_reference_arm(args)
     else:

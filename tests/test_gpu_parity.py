@@ -332,3 +332,35 @@ def test_shifted_image_shifts_keypoints(ctx):
     sb = {(int(k >> 24), int((k >> 12) & 0xFFF) - dx, int(k & 0xFFF) - dy): tuple(v)
           for k, v in zip(kb[inside(kb, dx, dy)], db[inside(kb, dx, dy)])}
     assert len(sa) > 50 and sa == sb
+
+
+def test_concurrent_contexts(oracle):
+    """The reference is re-entrant and safe to call concurrently on disjoint buffers:
+    one pislam_ctx per host thread, four threads hammering fused and literal calls at once."""
+    import threading
+    lays = [pyramid_layout(320, 240, nlevels=4), VGA]
+    errors = []
+
+    def work(t):
+        try:
+            lay = lays[t % 2]
+            stack = synthetic_stack(lay, 300 + t)
+            okp, olv, odesc = oracle_pyramid(oracle, stack, lay, log_bucket=4, bucket_limit=3)
+            with api.Context(0) as c:
+                for _ in range(10):
+                    kp, lv, desc = c.extract_pyramid(stack, api.make_desc(lay, log_bucket=4, bucket_limit=3), cap=4096)
+                    assert np.array_equal(kp, okp) and np.array_equal(desc, odesc)
+                    out = np.zeros_like(stack)
+                    c.fastDetect(lay.widths[0], lay.heights[0], stack, out, 20)
+                    c.fastScoreHarris(lay.widths[0], lay.heights[0], stack, 1 << 15, out)
+                    k0 = c.fastExtract(lay.widths[0], lay.heights[0], out, logBucketSize=4, bucketLimit=3)
+                    assert np.array_equal(k0, okp[olv == 0])
+        except Exception as e:  # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
