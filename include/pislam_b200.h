@@ -91,6 +91,17 @@ int pislam_b200_brief_describe(pislam_ctx* ctx, const uint8_t* img, int vstep, i
 int pislam_b200_orb_compute(pislam_ctx* ctx, const uint8_t* img, int vstep, int rows, const uint32_t* kp,
                             int n, int words, uint32_t* desc, uint8_t* angles);
 
+/* ---- pyramid-preparation helpers (not on the ORB hot path; host buffers) -----------------------
+ * pislam::gaussian5x5<vstep>(width,height,img,out)      reference Gaussian.h:48-72 (semantics of its test
+ *                                                       model test/GaussianTest.cpp:159-215); width,height >= 3
+ * pislam::bilinear7_8<vstep>(width,height,img,out)      reference Bilinear.h:42-150
+ * pislam::bilinear13_16<vstep>(width,height,img,out)    reference Bilinear.h:165-321
+ * img and out may be the same buffer.  The resamplers read whole 8x8 / 16x16 blocks: like the reference
+ * they need the image padded to a multiple of 8 / 16 rows and columns (inside the pitch). */
+int pislam_b200_gaussian5x5(pislam_ctx* ctx, const uint8_t* img, uint8_t* out, int vstep, int width, int height);
+int pislam_b200_bilinear7_8(pislam_ctx* ctx, const uint8_t* img, uint8_t* out, int vstep, int width, int height);
+int pislam_b200_bilinear13_16(pislam_ctx* ctx, const uint8_t* img, uint8_t* out, int vstep, int width, int height);
+
 /* ---- fused whole-pyramid path (the caller loop of reference demo/demo.cpp:77-101) ----------- */
 typedef struct pislam_pyramid_desc {
   int vstep;   /* row pitch of the stack in bytes */

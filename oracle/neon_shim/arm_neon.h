@@ -72,6 +72,7 @@ typedef nv<uint8_t, 16> uint8x16_t;
 typedef nv<uint8_t, 8> uint8x8_t;
 typedef nv<int8_t, 8> int8x8_t;
 typedef nv<uint16_t, 8> uint16x8_t;
+typedef nv<uint16_t, 4> uint16x4_t;
 typedef nv<int16_t, 8> int16x8_t;
 typedef nv<uint32_t, 4> uint32x4_t;
 typedef nv<int32_t, 4> int32x4_t;
@@ -104,6 +105,9 @@ NV_REINTERPRET(vreinterpret_s32_s64, int32x2_t, int64x1_t)
 NV_REINTERPRET(vreinterpret_u32_s32, uint32x2_t, int32x2_t)
 NV_REINTERPRET(vreinterpret_s32_u32, int32x2_t, uint32x2_t)
 NV_REINTERPRET(vreinterpret_u32_f32, uint32x2_t, float32x2_t)
+NV_REINTERPRET(vreinterpret_u32_u8, uint32x2_t, uint8x8_t)
+NV_REINTERPRET(vreinterpret_u16_u64, uint16x4_t, uint64x1_t)
+NV_REINTERPRET(vreinterpret_u64_u16, uint64x1_t, uint16x4_t)
 #undef NV_REINTERPRET
 
 // ---- loads / stores / dup / lane ------------------------------------------
@@ -232,5 +236,36 @@ static inline float nv_recpe(float x) {
   return r;
 }
 static inline float32x4_t vrecpeq_f32(const float32x4_t& a) { float32x4_t r; for (int i = 0; i < 4; ++i) r.v[i] = nv_recpe(a.v[i]); return r; }
+
+// ---- Bilinear.h (pyramid helpers: 7/8 and 13/16 down-scaling) ------------------------------------
+static inline void vst1_u8(uint8_t* p, const uint8x8_t& a) { std::memcpy(p, a.v, 8); }
+#define vst1_lane_u8(p, a, lane) ((p)[0] = (a).v[(lane)])
+#define vst1_lane_u32(p, a, lane) nv_st1_lane_u32((p), (a), (lane))
+static inline void nv_st1_lane_u32(uint32_t* p, const uint32x2_t& a, int lane) { std::memcpy(p, &a.v[lane], 4); }
+static inline uint8x8_t vget_low_u8(const uint8x16_t& a) { uint8x8_t r; std::memcpy(r.v, a.v, 8); return r; }
+static inline uint8x8_t vget_high_u8(const uint8x16_t& a) { uint8x8_t r; std::memcpy(r.v, a.v + 8, 8); return r; }
+static inline uint16x4_t vget_low_u16(const uint16x8_t& a) { uint16x4_t r; std::memcpy(r.v, a.v, 8); return r; }
+static inline uint16x4_t vget_high_u16(const uint16x8_t& a) { uint16x4_t r; std::memcpy(r.v, a.v + 4, 8); return r; }
+static inline uint16x8_t vcombine_u16(const uint16x4_t& lo, const uint16x4_t& hi) {
+  uint16x8_t r; std::memcpy(r.v, lo.v, 8); std::memcpy(r.v + 4, hi.v, 8); return r; }
+static inline uint16x8_t vaddq_u16(const uint16x8_t& a, const uint16x8_t& b) { return a + b; }
+// VEXT: lanes n.. of a followed by lanes 0..n-1 of b
+#define vextq_u16(a, b, n) nv_extq_u16((a), (b), (n))
+static inline uint16x8_t nv_extq_u16(const uint16x8_t& a, const uint16x8_t& b, int n) {
+  uint16x8_t r; for (int i = 0; i < 8; ++i) r.v[i] = (i + n < 8) ? a.v[i + n] : b.v[i + n - 8]; return r; }
+// VRSHR: rounding shift right, the rounding add does not overflow the lane (computed wider)
+#define vrshrq_n_u16(a, n) nv_rshrq_u16((a), (n))
+static inline uint16x8_t nv_rshrq_u16(const uint16x8_t& a, int n) {
+  uint16x8_t r; for (int i = 0; i < 8; ++i) r.v[i] = (uint16_t)(((uint32_t)a.v[i] + (1u << (n - 1))) >> n); return r; }
+#define vmulq_lane_u16(a, v, lane) nv_mulq_lane_u16((a), (v), (lane))
+static inline uint16x8_t nv_mulq_lane_u16(const uint16x8_t& a, const uint16x4_t& v, int lane) {
+  uint16x8_t r; for (int i = 0; i < 8; ++i) r.v[i] = (uint16_t)((uint32_t)a.v[i] * (uint32_t)v.v[lane]); return r; }
+// VRADDHN: (a + b + 0x80) >> 8 on wrap-around 16-bit sums, narrowed to 8 bits
+static inline uint8x8_t vraddhn_u16(const uint16x8_t& a, const uint16x8_t& b) {
+  uint8x8_t r; for (int i = 0; i < 8; ++i) r.v[i] = (uint8_t)(((uint16_t)(a.v[i] + b.v[i] + 0x80u)) >> 8); return r; }
+// VSLI: shift b left by n and insert into a, keeping the low n bits of a
+#define vsli_n_u64(a, b, n) nv_sli_u64((a), (b), (n))
+static inline uint64x1_t nv_sli_u64(const uint64x1_t& a, const uint64x1_t& b, int n) {
+  uint64x1_t r; r.v[0] = (b.v[0] << n) | (a.v[0] & ((1ull << n) - 1ull)); return r; }
 
 #endif  // PISLAM_ORACLE_NEON_SHIM_H_

@@ -388,6 +388,78 @@ int po_extract_pyramid(const uint8_t* stack, int vstep, int nlevels, const int* 
   return n;
 }
 
+/* ------------------------------------------------------------------ pyramid helpers
+ * Gaussian.h:48-72 (the separable [1 4 6 4 1]/16 kernel built from rounding halving adds) is hand-written
+ * ARM assembly and cannot be built here; this follows the scalar model the reference's own test checks it
+ * against, test/GaussianTest.cpp:32,159-215: vertical pass, then horizontal pass, reflect-101 borders. */
+static inline int rhadd(int a, int b) { return (a >> 1) + (b >> 1) + ((a | b) & 1); }
+static inline int reflect101(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+static inline int gauss5(int a, int b, int c, int d, int e) {
+  int x = rhadd(a, e);
+  x = rhadd(x, c);
+  x = rhadd(x, c);
+  return rhadd(x, rhadd(b, d));
+}
+
+void po_gaussian5x5(const uint8_t* img, uint8_t* out, int vstep, int width, int height) {
+  uint8_t* tmp = (uint8_t*)malloc((size_t)width * height);
+  for (int y = 0; y < height; ++y)
+    for (int x = 0; x < width; ++x) {
+      int r[5];
+      for (int k = 0; k < 5; ++k) r[k] = img[(long)reflect101(y + k - 2, height) * vstep + x];
+      tmp[(long)y * width + x] = (uint8_t)gauss5(r[0], r[1], r[2], r[3], r[4]);
+    }
+  for (int y = 0; y < height; ++y)
+    for (int x = 0; x < width; ++x) {
+      int r[5];
+      for (int k = 0; k < 5; ++k) r[k] = tmp[(long)y * width + reflect101(x + k - 2, width)];
+      out[(long)y * vstep + x] = (uint8_t)gauss5(r[0], r[1], r[2], r[3], r[4]);
+    }
+  free(tmp);
+}
+
+/* Bilinear.h:42-150 (7/8) and :165-321 (13/16); scalar models test/BilinearTest.cpp:35,171-233.
+ * Blocks of B x B input pixels (B = 8 / 16, the image is padded to a multiple of B) give O x O outputs
+ * (O = 7 / 13) with fixed-point weights /256 and rounding shifts; block (bi,bj) lands at (O*bi, O*bj).
+ * The 7/8 variant stores 8 bytes per block row, so one extra zero byte follows the last block of a row
+ * (Bilinear.h:139-145: lane 7 of every row is 0). */
+static inline int rshr8(int a) { return (a >> 8) + ((a >> 7) & 1); }
+static int map13(int i) { return i + (i > 3) + (i > 8); } /* BilinearTest.cpp:196-204 */
+
+static void bilinear_blocks(const uint8_t* img, uint8_t* out, int vstep, int width, int height, int B, int O,
+                            const int* f, int use_map13) {
+  for (int i = 0, oi = 0; i < height; i += B, oi += O)
+    for (int j = 0, oj = 0; j < width; j += B, oj += O)
+      for (int y = 0; y < O; ++y)
+        for (int x = 0; x < O; ++x) {
+          const int yy = i + (use_map13 ? map13(y) : y), xx = j + (use_map13 ? map13(x) : x);
+          const uint8_t* p = img + (long)yy * vstep + xx;
+          const int h0 = rshr8(p[0] * f[x] + p[1] * f[O - 1 - x]);
+          const int h1 = rshr8(p[vstep] * f[x] + p[vstep + 1] * f[O - 1 - x]);
+          out[(long)(oi + y) * vstep + (oj + x)] = (uint8_t)rshr8(h0 * f[y] + h1 * f[O - 1 - y]);
+        }
+}
+
+void po_bilinear7_8(const uint8_t* img, uint8_t* out, int vstep, int width, int height) {
+  static const int f[7] = {238, 201, 165, 128, 91, 55, 18};
+  if (width <= 0 || height <= 0) return;
+  uint8_t* src = (uint8_t*)malloc((size_t)((height + 7) / 8 * 8 + 1) * vstep); /* img and out may alias */
+  memcpy(src, img, (size_t)((height + 7) / 8 * 8) * vstep);
+  bilinear_blocks(src, out, vstep, width, height, 8, 7, f, 0);
+  const int nby = (height + 7) / 8, nbx = (width + 7) / 8;
+  for (int y = 0; y < 7 * nby; ++y) out[(long)y * vstep + 7 * nbx] = 0;
+  free(src);
+}
+
+void po_bilinear13_16(const uint8_t* img, uint8_t* out, int vstep, int width, int height) {
+  static const int f[13] = {226, 167, 108, 49, 246, 187, 128, 69, 10, 207, 138, 89, 30};
+  if (width <= 0 || height <= 0) return;
+  uint8_t* src = (uint8_t*)malloc((size_t)((height + 15) / 16 * 16 + 1) * vstep);
+  memcpy(src, img, (size_t)((height + 15) / 16 * 16) * vstep);
+  bilinear_blocks(src, out, vstep, width, height, 16, 13, f, 1);
+  free(src);
+}
+
 /* ------------------------------------------------------------------ all-host-cores baseline */
 typedef struct {
   const uint8_t* stacks;

@@ -10,6 +10,7 @@
 //   atan2             Orb.h:310-387
 //   orbCompute        Orb.h:396-441 -> Brief.h:57-733
 //   briefDescribe     Brief.h:637-733
+//   bilinear7_8 / bilinear13_16   Bilinear.h:42-150, 165-321 (pyramid helpers, not on the hot path)
 // The reference takes vstep/border/bucket/words as template arguments; this
 // driver instantiates a fixed menu of them and dispatches at run time. A
 // combination outside the menu returns -1.
@@ -22,6 +23,7 @@
 #include "arm_neon.h"   // oracle/neon_shim
 #include "Fast.h"       // oracle/_ref/Fast.h (generated), includes reference Harris.h/Util.h
 #include "Orb.h"        // /root/reference/include/Orb.h, includes Brief.h
+#include "Bilinear.h"   // /root/reference/include/Bilinear.h (pyramid helper)
 
 #define REF_VSTEPS(X) X(640) X(1920) X(3840) X(128) X(96)
 #define REF_BORDERS(X, V) X(V, 16) X(V, 9) X(V, 4)
@@ -133,6 +135,22 @@ int ref_brief_describe(const uint8_t* img, int vstep, int x, int y, int rot, int
   }
   CASE(640, 8) CASE(1920, 8) CASE(3840, 8) CASE(128, 8) CASE(96, 8)
   CASE(128, 1) CASE(128, 4) CASE(128, 5)
+#undef CASE
+  return -1;
+}
+
+int ref_bilinear7_8(uint8_t* img, uint8_t* out, int vstep, int width, int height) {
+#define CASE(V) \
+  if (vstep == V) { pislam::bilinear7_8<V>(width, height, (uint8_t(*)[V])img, (uint8_t(*)[V])out); return 0; }
+  REF_VSTEPS(CASE)
+#undef CASE
+  return -1;
+}
+
+int ref_bilinear13_16(uint8_t* img, uint8_t* out, int vstep, int width, int height) {
+#define CASE(V) \
+  if (vstep == V) { pislam::bilinear13_16<V>(width, height, (uint8_t(*)[V])img, (uint8_t(*)[V])out); return 0; }
+  REF_VSTEPS(CASE)
 #undef CASE
   return -1;
 }

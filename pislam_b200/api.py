@@ -67,6 +67,9 @@ _SIGNATURES = {
                                              C.c_int, _u32p]),
     "pislam_b200_orb_compute": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, _u32p, C.c_int, C.c_int, _u32p,
                                           _u8p]),
+    "pislam_b200_gaussian5x5": (C.c_int, [C.c_void_p, _u8p, _u8p, C.c_int, C.c_int, C.c_int]),
+    "pislam_b200_bilinear7_8": (C.c_int, [C.c_void_p, _u8p, _u8p, C.c_int, C.c_int, C.c_int]),
+    "pislam_b200_bilinear13_16": (C.c_int, [C.c_void_p, _u8p, _u8p, C.c_int, C.c_int, C.c_int]),
     "pislam_b200_record_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "pislam_b200_record_kp_offset": (C.c_size_t, [C.c_int, C.c_int]),
     "pislam_b200_record_desc_offset": (C.c_size_t, [C.c_int, C.c_int]),
@@ -294,6 +297,25 @@ class Context:
         if descriptors is not None:
             descriptors.extend(int(v) for v in d.ravel())
         return (d, a[:len(kp)]) if want_angles else d
+
+    # ---- pyramid-preparation helpers (not on the hot path) ---------------------------------------------
+    def gaussian5x5(self, width, height, img, out):
+        """pislam::gaussian5x5<vstep>(width,height,img,out) -- Gaussian.h:48-72."""
+        _check_img(img)
+        _check_img(out, "out")
+        self._ok(self.lib.pislam_b200_gaussian5x5(self._h, _p(img, _u8p), _p(out, _u8p), img.shape[1], width, height))
+
+    def bilinear7_8(self, width, height, img, out):
+        """pislam::bilinear7_8<vstep>(width,height,img,out) -- Bilinear.h:42-150."""
+        _check_img(img)
+        _check_img(out, "out")
+        self._ok(self.lib.pislam_b200_bilinear7_8(self._h, _p(img, _u8p), _p(out, _u8p), img.shape[1], width, height))
+
+    def bilinear13_16(self, width, height, img, out):
+        """pislam::bilinear13_16<vstep>(width,height,img,out) -- Bilinear.h:165-321."""
+        _check_img(img)
+        _check_img(out, "out")
+        self._ok(self.lib.pislam_b200_bilinear13_16(self._h, _p(img, _u8p), _p(out, _u8p), img.shape[1], width, height))
 
     # ---- fused whole-pyramid path (the caller loop of demo/demo.cpp:77-101) -------------------------
     def extract_pyramid(self, stack, desc, cap=4096):

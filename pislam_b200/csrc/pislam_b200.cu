@@ -21,6 +21,7 @@
 #include "brief_pattern.h"
 #include "front_kernels.cuh"
 #include "orb_kernels.cuh"
+#include "pyramid_kernels.cuh"
 
 using namespace pb;
 
@@ -823,6 +824,60 @@ int pislam_b200_orb_compute(pislam_ctx* c, const uint8_t* img, int vstep, int ro
   if (angles) CK(cudaMemcpyAsync(angles, c->aux1.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return PISLAM_OK;
+}
+
+// ---- pyramid helpers (not on the hot path) ----------------------------------------------------------
+namespace {
+// img/out round-trip like the literal stages: only the bytes the reference writes change in `out`
+int pyramid_helper(pislam_ctx* c, const uint8_t* img, uint8_t* out, int vstep, int width, int height, int kind) {
+  if (!c || !img || !out || vstep < 1 || width < 1 || height < 1 || width > vstep) return PISLAM_ERR_INVALID_ARG;
+  CKS(set_device(c));
+  const int B = kind == 1 ? 8 : (kind == 2 ? 16 : 1);
+  const int rows_in = (height + B - 1) / B * B;  // the reference reads whole blocks (padded input)
+  if (kind == 0 && (width < 3 || height < 3)) return PISLAM_ERR_INVALID_ARG;
+  if (kind != 0 && (width + B - 1) / B * B > vstep) return PISLAM_ERR_INVALID_ARG;
+  const int out_rows = kind == 0 ? height : (kind == 1 ? 7 : 13) * ((height + B - 1) / B);  // rows the reference writes
+  const size_t in_bytes = (size_t)rows_in * vstep, out_bytes = (size_t)out_rows * vstep;
+  CK(c->img.reserve(in_bytes + 16, false, c->stream));
+  CK(c->out.reserve(out_bytes + 16, false, c->stream));
+  CK(cudaMemcpyAsync(c->img.p, img, in_bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->out.p, out, out_bytes, cudaMemcpyHostToDevice, c->stream));
+  if (kind == 0) {
+    const int tpitch = (width + 3) & ~3;
+    CK(c->aux0.reserve((size_t)tpitch * height + 16, false, c->stream));
+    const dim3 grid(((width + 3) / 4 + 127) / 128, height);
+    gaussian_vertical_kernel<<<grid, 128, 0, c->stream>>>(c->img.as<uint8_t>(), c->aux0.as<uint8_t>(), vstep, tpitch,
+                                                          width, height);
+    CKS(check_launch(c));
+    gaussian_horizontal_kernel<<<grid, 128, 0, c->stream>>>(c->aux0.as<uint8_t>(), c->out.as<uint8_t>(), vstep, tpitch,
+                                                            width, height);
+    CKS(check_launch(c));
+  } else {
+    const int nbx = (width + B - 1) / B, nby = (height + B - 1) / B;
+    const int O = kind == 1 ? 7 : 13;
+    const dim3 grid((O * nbx + 1 + 127) / 128, O * nby);
+    if (kind == 1)
+      bilinear_blocks_kernel<8, 7, false><<<grid, 128, 0, c->stream>>>(c->img.as<uint8_t>(), c->out.as<uint8_t>(), vstep,
+                                                                       nbx, nby, 1);
+    else
+      bilinear_blocks_kernel<16, 13, true><<<grid, 128, 0, c->stream>>>(c->img.as<uint8_t>(), c->out.as<uint8_t>(), vstep,
+                                                                        nbx, nby, 0);
+    CKS(check_launch(c));
+  }
+  CK(cudaMemcpyAsync(out, c->out.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return PISLAM_OK;
+}
+}  // namespace
+
+int pislam_b200_gaussian5x5(pislam_ctx* c, const uint8_t* img, uint8_t* out, int vstep, int width, int height) {
+  return pyramid_helper(c, img, out, vstep, width, height, 0);
+}
+int pislam_b200_bilinear7_8(pislam_ctx* c, const uint8_t* img, uint8_t* out, int vstep, int width, int height) {
+  return pyramid_helper(c, img, out, vstep, width, height, 1);
+}
+int pislam_b200_bilinear13_16(pislam_ctx* c, const uint8_t* img, uint8_t* out, int vstep, int width, int height) {
+  return pyramid_helper(c, img, out, vstep, width, height, 2);
 }
 
 // ---- fused path ---------------------------------------------------------------------------------------

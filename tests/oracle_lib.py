@@ -59,6 +59,9 @@ class _Lib:
         f.argtypes = [u8p, C.c_int, u32p, C.c_int, C.c_int, u32p]
         f = getattr(L, p + "brief_describe")
         f.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u32p]
+        for name in ("bilinear7_8", "bilinear13_16"):
+            f = getattr(L, p + name)
+            f.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int]
         for name in ("encode_fast",):
             f = getattr(L, p + name)
             f.argtypes = [C.c_uint32] * 3
@@ -117,6 +120,12 @@ class _Lib:
         self._f("orb_compute")(_p(img, u8p), img.shape[1], _p(kp, u32p), len(kp), words, _p(d, u32p))
         return d[:len(kp) * words].reshape(len(kp), words).copy()
 
+    def bilinear7_8(self, img, out, width, height):
+        self._f("bilinear7_8")(_p(img, u8p), _p(out, u8p), img.shape[1], width, height)
+
+    def bilinear13_16(self, img, out, width, height):
+        self._f("bilinear13_16")(_p(img, u8p), _p(out, u8p), img.shape[1], width, height)
+
     def brief_describe(self, img, x, y, rot, words=8, fill=0xdeadbeef):
         d = np.full(words, fill, np.uint32)
         self._f("brief_describe")(_p(img, u8p), img.shape[1], x, y, rot, words, _p(d, u32p))
@@ -139,6 +148,10 @@ class Oracle(_Lib):
                                        C.c_int, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, intp,
                                        u32p, u32p]
         L.po_extract_batch.restype = C.c_int
+
+    def gaussian5x5(self, img, out, width, height):
+        self.lib.po_gaussian5x5.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int]
+        self.lib.po_gaussian5x5(_p(img, u8p), _p(out, u8p), img.shape[1], width, height)
 
     def angle_bin(self, m10, m01):
         return int(self.lib.po_angle_bin(int(m10), int(m01)))

@@ -72,6 +72,8 @@ SIGNATURE_TU = r"""
 #include "pislam/Orb.h"
 #include "pislam/Brief.h"
 #include "pislam/Util.h"
+#include "pislam/Gaussian.h"
+#include "pislam/Bilinear.h"
 // exact function types of the reference's templates (vstep 640, border 16, words 8)
 typedef uint8_t Row[640];
 void (*p_detect)(const int, const int, Row*, Row*, int) = &pislam::fastDetect<640, 16>;
@@ -83,6 +85,9 @@ std::vector<int32_t> (*p_centroids)(Row*, const std::vector<uint32_t>&) = &pisla
 std::vector<uint8_t> (*p_atan2)(const std::vector<int32_t>&) = &pislam::atan2;
 void (*p_orb)(Row*, const std::vector<uint32_t>&, std::vector<uint32_t>&) = &pislam::orbCompute<640, 8>;
 void (*p_brief)(Row*, int, int, int, uint32_t*) = &pislam::briefDescribe<640, 8>;
+void (*p_gauss)(const int, const int, Row*, Row*) = &pislam::gaussian5x5<640>;     // Gaussian.h:48-50
+void (*p_b78)(const int, const int, Row*, Row*) = &pislam::bilinear7_8<640>;       // Bilinear.h:42-44
+void (*p_b1316)(const int, const int, Row*, Row*) = &pislam::bilinear13_16<640>;   // Bilinear.h:165-167
 uint32_t (*p_enc)(uint32_t, uint32_t, uint32_t) = &pislam::encodeFast;
 uint32_t (*p_renc)(uint32_t, uint32_t) = &pislam::rencodeFastScore;
 uint32_t (*p_dx)(uint32_t) = &pislam::decodeFastX;
