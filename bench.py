@@ -335,7 +335,7 @@ def run_gpu_arm(args):
     latency = None
     if rank == 0:
         roof = kernel_roofline(ctx, api, d_stacks, frame_bytes, F, desc, d_records, kpts_local, args.steps)
-        latency = single_frame_latency(ctx, frames[0], desc)
+        latency = single_frame_latency(ctx, h_stacks[0].numpy(), desc)  # pinned host frame
 
     if world > 1:
         t = torch.tensor([kpts_local, overflow], device="cuda", dtype=torch.int64)
@@ -397,8 +397,9 @@ def run_gpu_arm(args):
 
 
 def single_frame_latency(ctx, stack, desc, iters=200):
-    """One pyramid at a time through pislam_b200_extract_pyramid (host stack in, host keypoints + descriptors
-    out, blocking): the latency a per-frame caller such as the reference demo loop sees.  Wall clock, mean."""
+    """One pyramid at a time through pislam_b200_extract_pyramid (pinned host stack in, host keypoints +
+    descriptors out, blocking): the latency a per-frame caller such as the reference demo loop sees.  Wall clock,
+    mean."""
     stack = np.ascontiguousarray(stack)
     for _ in range(10):
         ctx.extract_pyramid(stack, desc, cap=CAP)

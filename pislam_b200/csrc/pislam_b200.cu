@@ -176,6 +176,8 @@ struct pislam_ctx {
   cudaEvent_t ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {};
   int pipeline_chunks = 4;
   bool trim_copies = true;
+  void* h_rec = nullptr;  // pinned staging for single-frame results
+  size_t h_rec_cap = 0;
   // optional per-kernel timing (bench.py roofline): events around each fused-path launch
   bool profiling = false;
   struct ProfSpan {
@@ -547,6 +549,7 @@ int pislam_b200_destroy(pislam_ctx* c) {
                     &c->piece_cnt, &c->piece_off, &c->stacks, &c->records, &c->hdr};
   for (DevBuf* b : bufs) b->release();
   if (c->d_brief) cudaFree(c->d_brief);
+  if (c->h_rec) cudaFreeHost(c->h_rec);
   if (c->d_brief48) cudaFree(c->d_brief48);
   for (int i = 0; i < pislam_ctx::kMaxChunks; ++i) {
     if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
@@ -976,18 +979,39 @@ int pislam_b200_extract_pyramid(pislam_ctx* c, const uint8_t* stack, const pisla
   }
   uint8_t* d_rec = c->records.as<uint8_t>();
   CKS(enqueue_extract(c, d_stack, frame_bytes, 1, d, cap, d_rec));
-  uint32_t header[REC_HEADER_WORDS];
-  CK(cudaMemcpyAsync(header, d_rec, sizeof(header), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  // one D2H of the whole (small) record into pinned staging, one sync, then scatter on the host
+  if (c->h_rec_cap < rec.bytes) {
+    if (c->h_rec) cudaFreeHost(c->h_rec);
+    c->h_rec = nullptr;
+    c->h_rec_cap = 0;
+    CK(cudaHostAlloc(&c->h_rec, rec.bytes, cudaHostAllocDefault));
+    c->h_rec_cap = rec.bytes;
+  }
+  const uint8_t* h = static_cast<const uint8_t*>(c->h_rec);
+  const size_t small = 1u << 20;  // large capacities: fetch the header first, then only the used part
+  if (rec.bytes <= small) {
+    CK(cudaMemcpyAsync(c->h_rec, d_rec, rec.bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  } else {
+    CK(cudaMemcpyAsync(c->h_rec, d_rec, REC_HEADER_WORDS * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  const uint32_t* header = reinterpret_cast<const uint32_t*>(h);
   *n = (int)header[1];
   if (header[1] > header[0]) return PISLAM_ERR_CAPACITY;
   const size_t m = header[0];
   if (m) {
-    CK(cudaMemcpyAsync(kp, d_rec + rec.kp_off, m * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (kp_level) CK(cudaMemcpyAsync(kp_level, d_rec + rec.level_off, m, cudaMemcpyDeviceToHost, c->stream));
-    if (descriptors && d->words > 0)
-      CK(cudaMemcpyAsync(descriptors, d_rec + rec.desc_off, m * 4 * d->words, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    if (rec.bytes > small) {
+      uint8_t* hw = static_cast<uint8_t*>(c->h_rec);
+      CK(cudaMemcpyAsync(hw + rec.kp_off, d_rec + rec.kp_off, m * 4, cudaMemcpyDeviceToHost, c->stream));
+      if (kp_level) CK(cudaMemcpyAsync(hw + rec.level_off, d_rec + rec.level_off, m, cudaMemcpyDeviceToHost, c->stream));
+      if (descriptors && d->words > 0)
+        CK(cudaMemcpyAsync(hw + rec.desc_off, d_rec + rec.desc_off, m * 4 * d->words, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+    }
+    memcpy(kp, h + rec.kp_off, m * 4);
+    if (kp_level) memcpy(kp_level, h + rec.level_off, m);
+    if (descriptors && d->words > 0) memcpy(descriptors, h + rec.desc_off, m * 4 * d->words);
   }
   return PISLAM_OK;
 }
