@@ -153,15 +153,50 @@ constexpr int A_GROUPS = (SC_H + A_ROWS - 1) / A_ROWS;  // 7
 constexpr int A_TASKS = A_COLS * A_GROUPS;          // 238 (word column, row group) tasks
 static_assert(A_GROUPS * A_ROWS + 6 <= PIX_H + 1, "phase A rows stay inside the staged tile");
 
+// Work-list capacities.  Natural images need ~130 candidates / ~50 corners per tile; the lists are sized for
+// 15x / 20x that and anything beyond is handled EXACTLY but slowly (inline, then a dense non-max scan), so that
+// adversarial tiles (noise, checkerboards) stay bit-exact while the common case keeps 18 KB of shared memory.
+constexpr int CAP_A = 2048;  // list A: FAST candidates, later non-zero scores (also hosts the 4 KB slot array)
+constexpr int CAP_B = 1024;  // list B: FAST corners, later NMS survivors (at most one per cell = 1024)
+static_assert(CAP_A * 2 >= NCELL * 4 && CAP_B >= NCELL, "list A hosts s_cell2; list B holds one survivor per cell");
+
+// Slow path of a corner that did not fit into list B: score it in place (rarely executed, kept out of line)
+__device__ __noinline__ void score_corner_inline(const uint8_t* s_pix, uint8_t* s_score, int idx, int dxo,
+                                                 bool scored, int32_t harris_t) {
+  const int ry = idx / SC_W, sx = idx - ry * SC_W;
+  const uint32_t code = scored ? harris_code_at(s_pix + (ry + 3) * PIX_W + dxo + 4 + sx, PIX_W, harris_t) : 0xffu;
+  if (code) s_score[idx] = (uint8_t)code;
+}
+// Slow path of a candidate that did not fit into list A: exact FAST-9 and score in place
+__device__ __noinline__ void test_candidate_inline(const uint8_t* s_pix, uint8_t* s_score, int idx, int dxo, int t,
+                                                   bool scored, int32_t harris_t) {
+  const int ry = idx / SC_W, sx = idx - ry * SC_W;
+  if (fast9_at(s_pix + (ry + 3) * PIX_W + dxo + 4 + sx, PIX_W, t))
+    score_corner_inline(s_pix, s_score, idx, dxo, scored, harris_t);
+}
+
+// warp_push that reports the reserved position instead of storing (the caller handles overflow)
+__device__ __forceinline__ uint32_t warp_reserve(bool want, uint32_t* counter) {
+  const uint32_t b = __ballot_sync(0xffffffffu, want);
+  if (b == 0) return 0u;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(b) - 1;
+  uint32_t pos = 0;
+  if (lane == leader) pos = atomicAdd(counter, (uint32_t)__popc(b));
+  pos = __shfl_sync(0xffffffffu, pos, leader);
+  return pos + __popc(b & ((1u << lane) - 1u));
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(NT) front_tile_kernel(const __grid_constant__ FrontParams P,
+__global__ void __launch_bounds__(NT, 10) front_tile_kernel(const __grid_constant__ FrontParams P,
                                                         const __grid_constant__ CUtensorMap tmap) {
   __shared__ __align__(128) uint8_t s_pix[PIX_H * PIX_W];
   __shared__ __align__(16) uint8_t s_score[SC_H * SC_W];
-  __shared__ __align__(16) uint16_t s_listA[SC_H * SC_W];  // FAST candidates (A->B), then non-zero scores (C->D)
-  __shared__ uint16_t s_listB[SC_H * SC_W];                // FAST corners (B->C), then NMS survivors (D->D2)
+  __shared__ __align__(16) uint16_t s_listA[CAP_A];  // FAST candidates (A->B), then non-zero scores (C->D)
+  __shared__ uint16_t s_listB[CAP_B];                // FAST corners (B->C), then NMS survivors (D->D2)
   __shared__ uint32_t s_occ[NCELL / 32], s_bm[NCELL / 32], s_pref[NCELL / 32 + 1];
   __shared__ uint32_t s_nA, s_nB, s_nC, s_nS, s_base;
+  __shared__ uint32_t s_dense;  // a list overflowed: scores were written in place, phase D scans every cell
   __shared__ __align__(8) uint64_t s_bar;
   // the slot arrays reuse buffers that are dead by then: the pixels after phase C, list A after phase D
   static_assert(sizeof(s_pix) >= NCELL * 4 && sizeof(s_listA) >= NCELL * 4, "slot arrays alias s_pix / s_listA");
@@ -195,6 +230,7 @@ __global__ void __launch_bounds__(NT) front_tile_kernel(const __grid_constant__ 
     s_nB = 0;
     s_nC = 0;
     s_nS = 0;
+    s_dense = 0;
   }
   if (tid < NCELL / 32) {
     s_bm[tid] = 0u;
@@ -219,7 +255,11 @@ __global__ void __launch_bounds__(NT) front_tile_kernel(const __grid_constant__ 
         cand = v != 0 && cxp >= 0 && cxp < TW && cyp >= 0 && cyp < TH && x0 + (cxp & ~1) < xs_end &&
                y0 + (cyp & ~1) < ys_end;
       }
-      warp_push(cand, (uint16_t)i, s_listA, &s_nC);
+      const uint32_t pos = warp_reserve(cand, &s_nC);
+      if (cand) {
+        if (pos < CAP_A) s_listA[pos] = (uint16_t)i;
+        else s_dense = 1u;
+      }
     }
   } else {
     for (int i = tid; i < SC_H * SC_W / 16; i += NT) reinterpret_cast<uint4*>(s_score)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -293,13 +333,20 @@ __global__ void __launch_bounds__(NT) front_tile_kernel(const __grid_constant__ 
       while (acc) {
         const int b = __ffs(acc) - 1;
         acc &= acc - 1;
-        s_listA[pos++] = (uint16_t)((r0 + (b & 7)) * SC_W + 4 * wx + (b >> 3));
+        const int idx = (r0 + (b & 7)) * SC_W + 4 * wx + (b >> 3);
+        if (pos < CAP_A) {
+          s_listA[pos] = (uint16_t)idx;
+        } else {  // list A is full (adversarial tile): decide and score this candidate right here
+          test_candidate_inline(s_pix, s_score, idx, dxo, t, (x + (b >> 3)) < xs_end, P.harris_t);
+          s_dense = 1u;
+        }
+        ++pos;
       }
     }
     __syncthreads();
 
     // ---- phase B: exact FAST-9 on the candidates (Fast.h:54-158) ---------------------------------
-    const int nA = (int)s_nA;
+    const int nA = min((int)s_nA, CAP_A);
     for (int base = 0; base < nA; base += NT) {
       const int i = base + tid;
       const int idx = i < nA ? s_listA[i] : 0;
@@ -307,12 +354,20 @@ __global__ void __launch_bounds__(NT) front_tile_kernel(const __grid_constant__ 
       const bool corner = i < nA && fast9_at(s_pix + (ry + 3) * PIX_W + dxo + 4 + sx, PIX_W, t);
       // columns >= w-border are never scored (Fast.h:172): they keep the raw 0xff flag
       const bool scored = (x0 - 4 + sx) < xs_end;
-      warp_push(corner, (uint16_t)(idx | (scored ? 0 : 0x8000)), s_listB, &s_nB);
+      const uint32_t pos = warp_reserve(corner, &s_nB);
+      if (corner) {
+        if (pos < CAP_B) {
+          s_listB[pos] = (uint16_t)(idx | (scored ? 0 : 0x8000));
+        } else {  // list B is full: score in place
+          score_corner_inline(s_pix, s_score, idx, dxo, scored, P.harris_t);
+          s_dense = 1u;
+        }
+      }
     }
     __syncthreads();
 
     // ---- phase C: Harris code of every flagged pixel (Fast.h:166-180, Harris.h:80-248) ------------
-    const int nB = (int)s_nB;
+    const int nB = min((int)s_nB, CAP_B);
     for (int base = 0; base < nB; base += NT) {
       const int i = base + tid;
       const uint32_t e = i < nB ? s_listB[i] : 0u;
@@ -336,25 +391,51 @@ __global__ void __launch_bounds__(NT) front_tile_kernel(const __grid_constant__ 
   // ---- phase D: non-max suppression of the non-zero scores (Fast.h:228-310) -------------------------
   // slot = position in the reference's output order inside the tile: row-major 2x2 cells (plain) or
   // band / bucket / position-in-bucket (bucketed; re-ranked by encoded value in phase D2)
-  const int nC = (int)s_nC;
-  for (int base = 0; base < nC; base += NT) {
-    const int i = base + tid;
-    const int idx = i < nC ? s_listA[i] : 0;
+  // records a surviving pixel (score-tile index idx) in its slot; returns the slot
+  auto emit = [&](int idx) -> int {
     const int ry = idx / SC_W, sx = idx - ry * SC_W;
-    const uint8_t* q = s_score + idx;
-    const bool surv = i < nC && nms_survives(q, SC_W);
-    int slot = 0;
-    if (surv) {
-      const int cx = (sx - 4) >> 1, cy = (ry - 1) >> 1;
-      slot = cy * CELLS_X + cx;
-      if (lb > 0) {
-        const int cbm = (1 << cb_log) - 1;
-        slot = ((cy >> cb_log) << (6 + cb_log)) + ((cx >> cb_log) << (2 * cb_log)) + ((cy & cbm) << cb_log) + (cx & cbm);
-      }
-      s_cell[slot] = encode_fast(q[0], x0 - 4 + sx, y0 - 1 + ry);
-      atomicOr((lb == 0 ? s_bm : s_occ) + (slot >> 5), 1u << (slot & 31));
+    const int cx = (sx - 4) >> 1, cy = (ry - 1) >> 1;
+    int slot = cy * CELLS_X + cx;
+    if (lb > 0) {
+      const int cbm = (1 << cb_log) - 1;
+      slot = ((cy >> cb_log) << (6 + cb_log)) + ((cx >> cb_log) << (2 * cb_log)) + ((cy & cbm) << cb_log) + (cx & cbm);
     }
-    if (lb > 0) warp_push(surv, (uint16_t)slot, s_listB, &s_nS);
+    s_cell[slot] = encode_fast(s_score[idx], x0 - 4 + sx, y0 - 1 + ry);
+    atomicOr((lb == 0 ? s_bm : s_occ) + (slot >> 5), 1u << (slot & 31));
+    return slot;
+  };
+  if (!s_dense) {
+    const int nC = (int)s_nC;
+    for (int base = 0; base < nC; base += NT) {
+      const int i = base + tid;
+      const int idx = i < nC ? s_listA[i] : 0;
+      const bool surv = i < nC && nms_survives(s_score + idx, SC_W);
+      const int slot = surv ? emit(idx) : 0;
+      if (lb > 0) {
+        const uint32_t pos = warp_reserve(surv, &s_nS);
+        if (surv) s_listB[pos] = (uint16_t)slot;  // at most one survivor per cell: pos < CAP_B
+      }
+    }
+  } else {
+    // a work list overflowed on this tile: visit every 2x2 cell (the first survivor in raster order, if any)
+    for (int base = 0; base < NCELL; base += NT) {
+      const int c = base + tid;
+      const int cx = c & (CELLS_X - 1), cy = c >> 6;
+      int idx = -1;
+      if (x0 + 2 * cx < xs_end && y0 + 2 * cy < ys_end) {
+        const int i0 = (1 + 2 * cy) * SC_W + 4 + 2 * cx;
+        if (nms_survives(s_score + i0, SC_W)) idx = i0;
+        else if (nms_survives(s_score + i0 + 1, SC_W)) idx = i0 + 1;
+        else if (nms_survives(s_score + i0 + SC_W, SC_W)) idx = i0 + SC_W;
+        else if (nms_survives(s_score + i0 + SC_W + 1, SC_W)) idx = i0 + SC_W + 1;
+      }
+      const bool surv = idx >= 0;
+      const int slot = surv ? emit(idx) : 0;
+      if (lb > 0) {
+        const uint32_t pos = warp_reserve(surv, &s_nS);
+        if (surv) s_listB[pos] = (uint16_t)slot;
+      }
+    }
   }
   __syncthreads();
 

@@ -376,8 +376,10 @@ int enqueue_extract(pislam_ctx* c, const uint8_t* d_stacks, size_t frame_stride,
   if (g.ntiles > 0) {
     const dim3 grid(g.ntiles, nframes);
     span_begin(c, 0);
+    // occupancy experiments: extra (unused) dynamic shared memory per CTA
+    static const int pad = getenv("PISLAM_B200_DEBUG_SMEM_PAD") ? atoi(getenv("PISLAM_B200_DEBUG_SMEM_PAD")) : 0;
     if (tma_ok && make_tensor_map(c, &tmap, d_stacks, d->vstep, g.rows, nframes, frame_stride) == PISLAM_OK)
-      front_tile_kernel<MODE_TMA><<<grid, NT, 0, c->stream>>>(P, tmap);
+      front_tile_kernel<MODE_TMA><<<grid, NT, pad, c->stream>>>(P, tmap);
     else
       front_tile_kernel<MODE_LDG><<<grid, NT, 0, c->stream>>>(P, tmap);
     span_end(c);
