@@ -188,7 +188,7 @@ __device__ __forceinline__ uint32_t warp_reserve(bool want, uint32_t* counter) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(NT, 10) front_tile_kernel(const __grid_constant__ FrontParams P,
+__global__ void __launch_bounds__(NT, 9) front_tile_kernel(const __grid_constant__ FrontParams P,
                                                         const __grid_constant__ CUtensorMap tmap) {
   __shared__ __align__(128) uint8_t s_pix[PIX_H * PIX_W];
   __shared__ __align__(16) uint8_t s_score[SC_H * SC_W];
