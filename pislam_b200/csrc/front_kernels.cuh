@@ -330,17 +330,27 @@ __global__ void __launch_bounds__(NT, 9) front_tile_kernel(const __grid_constant
       uint32_t pos = 0;
       if (lane == last && incl) pos = atomicAdd(&s_nA, incl);
       pos = __shfl_sync(amask, pos, last) + incl - cnt;
-      while (acc) {
-        const int b = __ffs(acc) - 1;
-        acc &= acc - 1;
-        const int idx = (r0 + (b & 7)) * SC_W + 4 * wx + (b >> 3);
-        if (pos < CAP_A) {
-          s_listA[pos] = (uint16_t)idx;
-        } else {  // list A is full (adversarial tile): decide and score this candidate right here
-          test_candidate_inline(s_pix, s_score, idx, dxo, t, (x + (b >> 3)) < xs_end, P.harris_t);
-          s_dense = 1u;
+      const int idx0 = r0 * SC_W + 4 * wx;
+      if (pos + cnt <= CAP_A) {
+        // 20 predicated stores instead of a loop over the set bits (that loop ran with ~3 of 32 lanes busy)
+#pragma unroll
+        for (int i = 0; i < A_ROWS; ++i)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (acc & (1u << (8 * k + i))) s_listA[pos++] = (uint16_t)(idx0 + i * SC_W + k);
+      } else {  // list A is (nearly) full, adversarial tile: what does not fit is decided and scored right here
+        while (acc) {
+          const int b = __ffs(acc) - 1;
+          acc &= acc - 1;
+          const int idx = idx0 + (b & 7) * SC_W + (b >> 3);
+          if (pos < CAP_A) {
+            s_listA[pos] = (uint16_t)idx;
+          } else {
+            test_candidate_inline(s_pix, s_score, idx, dxo, t, (x + (b >> 3)) < xs_end, P.harris_t);
+            s_dense = 1u;
+          }
+          ++pos;
         }
-        ++pos;
       }
     }
     __syncthreads();
