@@ -31,18 +31,19 @@ def stale():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build_library(force=False, verbose=False):
-    if not force and not stale():
+def build_library(force=False, verbose=False, out=None, extra=()):
+    """`out` / `extra` build a variant for A/B runs (tools/gpu_front_ab.py), e.g. extra=["-DPB_FRONT_MIN_CTAS=8"]."""
+    if out is None and not force and not stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+    cmd = [_nvcc()] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", out or LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout)
     if verbose:
         print(r.stdout)
-    return LIB_PATH
+    return out or LIB_PATH
 
 
 if __name__ == "__main__":

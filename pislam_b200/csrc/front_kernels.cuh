@@ -120,16 +120,77 @@ __device__ __forceinline__ uint32_t bytes_gt(uint32_t d, uint32_t k7, uint32_t m
   return (d & s) | ((d | s) & m_or);
 }
 
-// Warp-aggregated append of one 16-bit item per participating lane to a shared list.
-__device__ __forceinline__ void warp_push(bool want, uint16_t item, uint16_t* list, uint32_t* counter) {
+// shared-memory operations on explicit 32-bit shared addresses
+__device__ __forceinline__ uint32_t atom_shared_add(uint32_t addr, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+  return old;
+}
+
+// Warp-aggregated reservation in a shared list: every lane of the warp calls it (uniform loops only); lane 0
+// adds the warp's count to the counter.  Returns the lane's position (meaningless when !want).
+__device__ __forceinline__ uint32_t warp_reserve(bool want, uint32_t* counter) {
   const uint32_t b = __ballot_sync(0xffffffffu, want);
-  if (b == 0) return;
+  if (b == 0) return 0u;
   const int lane = threadIdx.x & 31;
-  const int leader = __ffs(b) - 1;
   uint32_t pos = 0;
-  if (lane == leader) pos = atomicAdd(counter, (uint32_t)__popc(b));
-  pos = __shfl_sync(0xffffffffu, pos, leader);
-  if (want) list[pos + __popc(b & ((1u << lane) - 1u))] = item;
+  if (lane == 0) pos = atom_shared_add(smem_u32(counter), (uint32_t)__popc(b));
+  pos = __shfl_sync(0xffffffffu, pos, 0);
+  return pos + __popc(b & ((1u << lane) - 1u));
+}
+// append of one 16-bit item per participating lane
+__device__ __forceinline__ void warp_push(bool want, uint16_t item, uint16_t* list, uint32_t* counter) {
+  const uint32_t pos = warp_reserve(want, counter);
+  if (want) list[pos] = item;
+}
+
+// Superset form of bytes_gt for t < 128, K = (0x7f - t) * 0x01010101: bit 7 of d | (d + K).  Bytes >= 128 pass
+// through d itself; for bytes < 128 the byte sum d + (127 - t) + carry-in stays below 256, so bit 7 says
+// d + carry-in > t.  A carry from the byte below (that byte is >= 129 + t) can only turn a tie d == t into a
+// pass, never a pass into a fail: fine for a pre-test whose survivors are tested exactly (1 extra candidate in
+// 200 000 on the synthetic set), and it saves the per-byte masking.
+__device__ __forceinline__ uint32_t bytes_gt_loose(uint32_t d, uint32_t K) { return d | (d + K); }
+
+// Phase-A arithmetic for one word column `c` (row pitch PIX_W/4 words): rows 0..10 of the column and the words
+// left/right of rows 3..7.  Bit 8k+i of the result: pixel k of row i+3 passes (N or S) and (E or W).
+template <bool T_LT_128>
+__device__ __forceinline__ uint32_t pretest_rows(const uint32_t* c, int t) {
+  constexpr int PW = (TW + 32) / 4, R = 5;
+  const uint32_t K = (0x7fu - (uint32_t)(t & 0x7f)) * 0x01010101u;
+  uint32_t I[R + 6];
+#pragma unroll
+  for (int q = 0; q < R + 6; ++q) I[q] = c[q * PW];
+  uint32_t V[R + 3];
+#pragma unroll
+  for (int q = 0; q < R + 3; ++q) {
+    const uint32_t d = __vabsdiffu4(I[q + 3], I[q]);
+    V[q] = T_LT_128 ? bytes_gt_loose(d, K) : bytes_gt(d, K, 0u);
+  }
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const uint32_t C = I[i + 3];
+    const uint32_t* cr = c + (i + 3) * PW;
+    const uint32_t dE = __vabsdiffu4(__funnelshift_r(C, cr[1], 24), C);   // pixels x+3 .. x+6 against x .. x+3
+    const uint32_t dW = __vabsdiffu4(__funnelshift_r(cr[-1], C, 8), C);   // pixels x-3 .. x
+    const uint32_t ew = T_LT_128 ? (bytes_gt_loose(dE, K) | bytes_gt_loose(dW, K))
+                                 : (bytes_gt(dE, K, 0u) | bytes_gt(dW, K, 0u));
+    const uint32_t m = (V[i] | V[i + 3]) & ew;
+    acc |= (m >> (7 - i)) & (0x01010101u << i);
+  }
+  return acc;
+}
+
+// if (bits & bit) { *(uint16_t*)addr = v; addr += 2; }  as two predicated instructions
+__device__ __forceinline__ void push_if_bit(uint32_t& addr, uint32_t bits, uint32_t bit, uint16_t v) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b32 m;\n\t"
+      "and.b32 m, %2, %3;\n\t"
+      "setp.ne.u32 p, m, 0;\n\t"
+      "@p st.shared.u16 [%0], %1;\n\t"
+      "@p add.u32 %0, %0, 2;\n\t}"
+      : "+r"(addr)
+      : "h"(v), "r"(bits), "r"(bit));
 }
 
 // Non-max rule of Fast.h:264-310 in position-independent form: a pixel survives iff it is >= the four
@@ -152,6 +213,7 @@ constexpr int A_ROWS = 5;                           // rows per phase-A thread
 constexpr int A_GROUPS = (SC_H + A_ROWS - 1) / A_ROWS;  // 7
 constexpr int A_TASKS = A_COLS * A_GROUPS;          // 238 (word column, row group) tasks
 static_assert(A_GROUPS * A_ROWS + 6 <= PIX_H + 1, "phase A rows stay inside the staged tile");
+static_assert(A_ROWS == 5, "pretest_rows and the 5-bit row mask are written for 5 rows per task");
 
 // Work-list capacities.  Natural images need ~130 candidates / ~50 corners per tile; the lists are sized for
 // 15x / 20x that and anything beyond is handled EXACTLY but slowly (inline, then a dense non-max scan), so that
@@ -175,27 +237,18 @@ __device__ __noinline__ void test_candidate_inline(const uint8_t* s_pix, uint8_t
     score_corner_inline(s_pix, s_score, idx, dxo, scored, harris_t);
 }
 
-// warp_push that reports the reserved position instead of storing (the caller handles overflow)
-__device__ __forceinline__ uint32_t warp_reserve(bool want, uint32_t* counter) {
-  const uint32_t b = __ballot_sync(0xffffffffu, want);
-  if (b == 0) return 0u;
-  const int lane = threadIdx.x & 31;
-  const int leader = __ffs(b) - 1;
-  uint32_t pos = 0;
-  if (lane == leader) pos = atomicAdd(counter, (uint32_t)__popc(b));
-  pos = __shfl_sync(0xffffffffu, pos, leader);
-  return pos + __popc(b & ((1u << lane) - 1u));
-}
-
+#ifndef PB_FRONT_MIN_CTAS
+#define PB_FRONT_MIN_CTAS 9  // 56 registers; 8 (64) and 10 (48, spills) measured slower
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(NT, 9) front_tile_kernel(const __grid_constant__ FrontParams P,
+__global__ void __launch_bounds__(NT, PB_FRONT_MIN_CTAS) front_tile_kernel(const __grid_constant__ FrontParams P,
                                                         const __grid_constant__ CUtensorMap tmap) {
   __shared__ __align__(128) uint8_t s_pix[PIX_H * PIX_W];
   __shared__ __align__(16) uint8_t s_score[SC_H * SC_W];
   __shared__ __align__(16) uint16_t s_listA[CAP_A];  // FAST candidates (A->B), then non-zero scores (C->D)
   __shared__ uint16_t s_listB[CAP_B];                // FAST corners (B->C), then NMS survivors (D->D2)
-  __shared__ uint32_t s_occ[NCELL / 32], s_bm[NCELL / 32], s_pref[NCELL / 32 + 1];
-  __shared__ uint32_t s_nA, s_nB, s_nC, s_nS, s_base;
+  __shared__ uint32_t s_occ[NCELL / 32], s_bm[NCELL / 32];
+  __shared__ uint32_t s_nA, s_nB, s_nC, s_nS;
   __shared__ uint32_t s_dense;  // a list overflowed: scores were written in place, phase D scans every cell
   __shared__ __align__(8) uint64_t s_bar;
   // the slot arrays reuse buffers that are dead by then: the pixels after phase C, list A after phase D
@@ -282,44 +335,30 @@ __global__ void __launch_bounds__(NT, 9) front_tile_kernel(const __grid_constant
     // ---- phase A: SWAR pre-test on the four compass ring pixels ---------------------------------
     // A 9-arc always contains two neighbouring compass points (ring 1,5,9,13), so a corner needs
     // |p-c| > t on (N or S) and on (E or W).  One thread owns a word column (4 pixels) and 5 rows:
-    // V(q) = |I[q+3]-I[q]| > t serves as the S test of row q and the N test of row q+3.
+    // |I[q+3]-I[q]| > t serves as the S test of row q and the N test of row q+3.  The test only has to be
+    // a superset of the corners (phase B is exact), which buys the carry-tolerant compare of bytes_gt_loose.
     const int t = P.fast_t & 0xff;  // Fast.h:58 keeps the low byte
+    const uint32_t listA_s = smem_u32(s_listA), nA_s = smem_u32(&s_nA);
+    const int xlo_rel = max(B, x0 - 1) - (x0 - 4), xhi_rel = min(L.xend, x0 + TW + 1) - (x0 - 4);
+    const int ylo_rel = B - (y0 - 1), yhi_rel = min(ys_end - (y0 - 1), SC_H);
     for (int task = tid; task < ((A_TASKS + 31) & ~31); task += NT) {
-      if (task >= A_TASKS) break;  // whole lanes beyond the last task: the partial warp is handled below
+      // tasks A_TASKS.. of the last warp fall below the score tile (no valid row): they only take part in the scan
       const int g = task / A_COLS, wx = task - g * A_COLS;
       const int r0 = g * A_ROWS;
-      const int x = x0 - 4 + 4 * wx;
-      const int xlo = max(B, x0 - 1), xhi = min(L.xend, x0 + TW + 1);  // columns whose flag matters here
-      const int nlo = min(max(xlo - x, 0), 4), nhi = min(max(xhi - x, 0), 4);
+      // columns / rows of the task whose flag matters here, relative to the task's first pixel (x0-4+4wx, y0-1+r0)
+      const int nlo = min(max(xlo_rel - 4 * wx, 0), 4), nhi = min(max(xhi_rel - 4 * wx, 0), 4);
+      const int ilo = min(max(ylo_rel - r0, 0), A_ROWS), ihi = min(max(yhi_rel - r0, 0), A_ROWS);
       uint32_t acc = 0;  // bit 8k+i: pixel k of row r0+i is a candidate
-      if (nlo < nhi) {
+      if (nlo < nhi && ilo < ihi) {
         const uint32_t colmask = (0x01010101u << (8 * nlo)) & (0x01010101u >> (8 * (4 - nhi)));
-        const uint32_t k7 = (0x7fu - (uint32_t)(t & 0x7f)) * 0x01010101u;
-        const uint32_t t_lt_128 = t < 128 ? 0xffffffffu : 0u;
+        const uint32_t rowbits = ((1u << ihi) - 1u) & ~((1u << ilo) - 1u);
         const uint32_t* c = reinterpret_cast<const uint32_t*>(s_pix) + r0 * (PIX_W / 4) + (dxo >> 2) + 1 + wx;
-        uint32_t I[A_ROWS + 6];
-#pragma unroll
-        for (int q = 0; q < A_ROWS + 6; ++q) I[q] = c[q * (PIX_W / 4)];
-        uint32_t V[A_ROWS + 3];
-#pragma unroll
-        for (int q = 0; q < A_ROWS + 3; ++q) V[q] = bytes_gt(__vabsdiffu4(I[q + 3], I[q]), k7, t_lt_128);
-#pragma unroll
-        for (int i = 0; i < A_ROWS; ++i) {
-          const int y = y0 - 1 + r0 + i;
-          const uint32_t C = I[i + 3];
-          const uint32_t* cr = c + (i + 3) * (PIX_W / 4);
-          const uint32_t E = __funnelshift_r(C, cr[1], 24);   // pixels x+3 .. x+6
-          const uint32_t W = __funnelshift_r(cr[-1], C, 8);   // pixels x-3 .. x
-          const uint32_t ew = bytes_gt(__vabsdiffu4(E, C), k7, t_lt_128) | bytes_gt(__vabsdiffu4(W, C), k7, t_lt_128);
-          uint32_t m = ((V[i] | V[i + 3]) & ew) >> 7;
-          if (r0 + i >= SC_H || y < B || y >= ys_end) m = 0;
-          acc |= (m & colmask) << i;
-        }
+        acc = (t < 128 ? pretest_rows<true>(c, t) : pretest_rows<false>(c, t)) & (colmask * rowbits);
       }
-      // one list reservation per warp for all rows
-      // the last warp of phase A is partial (threads 224..237): its highest lane reserves
-      const int last = min(31, A_TASKS - 1 - (task & ~31));
-      const uint32_t amask = 0xffffffffu >> (31 - last);
+      // one list reservation per warp for all rows; a warp without candidates (30 % of them) skips it
+      constexpr int last = 31;
+      constexpr uint32_t amask = 0xffffffffu;
+      if (__ballot_sync(amask, acc != 0u) == 0u) continue;
       const uint32_t cnt = (uint32_t)__popc(acc);
       uint32_t incl = cnt;
 #pragma unroll
@@ -328,16 +367,17 @@ __global__ void __launch_bounds__(NT, 9) front_tile_kernel(const __grid_constant
         if (lane >= d) incl += o;
       }
       uint32_t pos = 0;
-      if (lane == last && incl) pos = atomicAdd(&s_nA, incl);
+      if (lane == last) pos = atom_shared_add(nA_s, incl);
       pos = __shfl_sync(amask, pos, last) + incl - cnt;
       const int idx0 = r0 * SC_W + 4 * wx;
       if (pos + cnt <= CAP_A) {
-        // 20 predicated stores instead of a loop over the set bits (that loop ran with ~3 of 32 lanes busy)
+        // 20 predicated stores (a loop over the set bits runs with ~3 of 32 lanes busy); explicit shared
+        // addresses: the compiler otherwise rebuilds the shared window base inside every predicated block
+        uint32_t a = listA_s + 2u * pos;
 #pragma unroll
         for (int i = 0; i < A_ROWS; ++i)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (acc & (1u << (8 * k + i))) s_listA[pos++] = (uint16_t)(idx0 + i * SC_W + k);
+          for (int k = 0; k < 4; ++k) push_if_bit(a, acc, 1u << (8 * k + i), (uint16_t)(idx0 + i * SC_W + k));
       } else {  // list A is (nearly) full, adversarial tile: what does not fit is decided and scored right here
         while (acc) {
           const int b = __ffs(acc) - 1;
@@ -346,7 +386,7 @@ __global__ void __launch_bounds__(NT, 9) front_tile_kernel(const __grid_constant
           if (pos < CAP_A) {
             s_listA[pos] = (uint16_t)idx;
           } else {
-            test_candidate_inline(s_pix, s_score, idx, dxo, t, (x + (b >> 3)) < xs_end, P.harris_t);
+            test_candidate_inline(s_pix, s_score, idx, dxo, t, (x0 - 4 + 4 * wx + (b >> 3)) < xs_end, P.harris_t);
             s_dense = 1u;
           }
           ++pos;
@@ -482,45 +522,39 @@ __global__ void __launch_bounds__(NT, 9) front_tile_kernel(const __grid_constant
   }
 
   // ---- phase E: rank by slot = popcount prefix over the slot bitmap; one staging segment per tile ----
+  // One warp: lane w owns bitmap word w (a tile keeps a handful of keypoints; 128 threads sweeping all 1024
+  // slots cost more than the few set bits).
   if (tid < 32) {
-    const uint32_t pc = (uint32_t)__popc(s_bm[tid]);
+    const uint32_t w = s_bm[tid];
+    const uint32_t pc = (uint32_t)__popc(w);
     uint32_t incl = pc;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
       if (lane >= d) incl += o;
     }
-    s_pref[tid + 1] = incl;
-    if (tid == 0) s_pref[0] = 0u;
-    if (tid == 31) s_base = incl ? atomicAdd(P.stage_count + frame, incl) : 0u;
-  }
-  __syncthreads();
-  const uint32_t base = s_base;
-  for (int g = tid; g < NCELL / 4; g += NT) {  // slots 4g .. 4g+3
-    const uint32_t w = s_bm[g >> 3];
-    const int sh = (g & 7) * 4;
-    const uint32_t nib = (w >> sh) & 15u;
-    if (nib) {
-      uint32_t* stage = P.stage + (size_t)frame * P.cap;
-      uint32_t pos = base + s_pref[g >> 3] + (uint32_t)__popc(w & ((1u << sh) - 1u));
-      const uint4 v = reinterpret_cast<const uint4*>(cells)[g];
-      const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if ((nib >> j) & 1u) {
-          if (pos < (uint32_t)P.cap) stage[pos] = vv[j];
-          ++pos;
-        }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t base = 0;
+    if (lane == 31 && total) base = atomicAdd(P.stage_count + frame, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    const uint32_t excl = incl - pc;
+    uint32_t* stage = P.stage + (size_t)frame * P.cap;
+    uint32_t pos = base + excl;
+    for (uint32_t bits = w; bits; bits &= bits - 1u) {
+      if (pos < (uint32_t)P.cap) stage[pos] = cells[tid * 32 + (__ffs(bits) - 1)];
+      ++pos;
     }
-  }
-  // a segment is one cell row (64 slots = 2 bitmap words) or one bucket band (64 << cb_log slots)
-  const int seg_words = 2 << cb_log;
-  const int nseg = (NCELL / 32) / seg_words;
-  if (tid < nseg) {
-    const uint32_t a = s_pref[tid * seg_words], b = s_pref[(tid + 1) * seg_words];
-    const size_t pi = (size_t)frame * P.npieces + td.piece0 + tid * L.ntile_cols;
-    P.piece_cnt[pi] = b - a;
-    P.piece_off[pi] = base + a;
+    // a segment is one cell row (64 slots = 2 bitmap words) or one bucket band (64 << cb_log slots)
+    const int seg_words = 2 << cb_log;
+    const int nseg = (NCELL / 32) / seg_words;
+    const uint32_t a = __shfl_sync(0xffffffffu, excl, (tid * seg_words) & 31);
+    const uint32_t bnext = __shfl_sync(0xffffffffu, excl, ((tid + 1) * seg_words) & 31);
+    const uint32_t b = (tid + 1) * seg_words >= NCELL / 32 ? total : bnext;
+    if (tid < nseg) {
+      const size_t pi = (size_t)frame * P.npieces + td.piece0 + tid * L.ntile_cols;
+      P.piece_cnt[pi] = b - a;
+      P.piece_off[pi] = base + a;
+    }
   }
 }
 
