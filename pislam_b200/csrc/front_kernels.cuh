@@ -120,22 +120,28 @@ __device__ __forceinline__ uint32_t bytes_gt(uint32_t d, uint32_t k7, uint32_t m
   return (d & s) | ((d | s) & m_or);
 }
 
-// shared-memory operations on explicit 32-bit shared addresses
-__device__ __forceinline__ uint32_t atom_shared_add(uint32_t addr, uint32_t v) {
-  uint32_t old;
-  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
-  return old;
+// One lane of the (fully converged) warp adds `v` to the shared counter at `addr`; every lane gets the old value.
+// elect.sync keeps ptxas from wrapping the atomic into its generic warp-aggregation sequence (17 instructions
+// per call site, 3.6 % of the kernel's instructions before), REDUX broadcasts the result.
+__device__ __forceinline__ uint32_t warp_atom_shared_add(uint32_t addr, uint32_t v) {
+  uint32_t old = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "@p atom.shared.add.u32 %0, [%1], %2;\n\t}"
+      : "+r"(old)
+      : "r"(addr), "r"(v)
+      : "memory");
+  return __reduce_max_sync(0xffffffffu, old);
 }
 
-// Warp-aggregated reservation in a shared list: every lane of the warp calls it (uniform loops only); lane 0
-// adds the warp's count to the counter.  Returns the lane's position (meaningless when !want).
+// Warp-aggregated reservation in a shared list: every lane of the warp calls it (uniform loops only).
+// Returns the lane's position (meaningless when !want).
 __device__ __forceinline__ uint32_t warp_reserve(bool want, uint32_t* counter) {
   const uint32_t b = __ballot_sync(0xffffffffu, want);
   if (b == 0) return 0u;
   const int lane = threadIdx.x & 31;
-  uint32_t pos = 0;
-  if (lane == 0) pos = atom_shared_add(smem_u32(counter), (uint32_t)__popc(b));
-  pos = __shfl_sync(0xffffffffu, pos, 0);
+  const uint32_t pos = warp_atom_shared_add(smem_u32(counter), (uint32_t)__popc(b));
   return pos + __popc(b & ((1u << lane) - 1u));
 }
 // append of one 16-bit item per participating lane
@@ -221,6 +227,7 @@ static_assert(A_ROWS == 5, "pretest_rows and the 5-bit row mask are written for 
 constexpr int CAP_A = 2048;  // list A: FAST candidates, later non-zero scores (also hosts the 4 KB slot array)
 constexpr int CAP_B = 1024;  // list B: FAST corners, later NMS survivors (at most one per cell = 1024)
 static_assert(CAP_A * 2 >= NCELL * 4 && CAP_B >= NCELL, "list A hosts s_cell2; list B holds one survivor per cell");
+static_assert(CAP_B * 2 >= ((A_TASKS + 31) & ~31) * 8, "list B hosts the phase-A task list (8 bytes per task)");
 
 // Slow path of a corner that did not fit into list B: score it in place (rarely executed, kept out of line)
 __device__ __noinline__ void score_corner_inline(const uint8_t* s_pix, uint8_t* s_score, int idx, int dxo,
@@ -237,8 +244,11 @@ __device__ __noinline__ void test_candidate_inline(const uint8_t* s_pix, uint8_t
     score_corner_inline(s_pix, s_score, idx, dxo, scored, harris_t);
 }
 
+#ifndef PB_TASK_LIST
+#define PB_TASK_LIST 1  // phase A compacts non-empty tasks before expanding their bits (0: expand per warp round)
+#endif
 #ifndef PB_FRONT_MIN_CTAS
-#define PB_FRONT_MIN_CTAS 9  // 56 registers; 8 (64) and 10 (48, spills) measured slower
+#define PB_FRONT_MIN_CTAS 10  // 48 registers (32 B of spills); measured: 8 CTAs/SM +3 %, 9 +0.7 %, 11-12 +4 % (spills)
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(NT, PB_FRONT_MIN_CTAS) front_tile_kernel(const __grid_constant__ FrontParams P,
@@ -246,9 +256,11 @@ __global__ void __launch_bounds__(NT, PB_FRONT_MIN_CTAS) front_tile_kernel(const
   __shared__ __align__(128) uint8_t s_pix[PIX_H * PIX_W];
   __shared__ __align__(16) uint8_t s_score[SC_H * SC_W];
   __shared__ __align__(16) uint16_t s_listA[CAP_A];  // FAST candidates (A->B), then non-zero scores (C->D)
-  __shared__ uint16_t s_listB[CAP_B];                // FAST corners (B->C), then NMS survivors (D->D2)
+  __shared__ __align__(8) uint16_t s_listB[CAP_B];   // FAST corners (B->C), then NMS survivors (D->D2); hosts the
+                                                     // phase-A task list before that
   __shared__ uint32_t s_occ[NCELL / 32], s_bm[NCELL / 32];
-  __shared__ uint32_t s_nA, s_nB, s_nC, s_nS;
+  __shared__ uint32_t s_vmcol[A_COLS], s_vmrow[A_GROUPS + 1];  // phase-A validity masks per word column / row group
+  __shared__ uint32_t s_nA, s_nB, s_nC, s_nS, s_nT;
   __shared__ uint32_t s_dense;  // a list overflowed: scores were written in place, phase D scans every cell
   __shared__ __align__(8) uint64_t s_bar;
   // the slot arrays reuse buffers that are dead by then: the pixels after phase C, list A after phase D
@@ -283,11 +295,24 @@ __global__ void __launch_bounds__(NT, PB_FRONT_MIN_CTAS) front_tile_kernel(const
     s_nB = 0;
     s_nC = 0;
     s_nS = 0;
+    s_nT = 0;
     s_dense = 0;
   }
   if (tid < NCELL / 32) {
     s_bm[tid] = 0u;
     s_occ[tid] = 0u;
+  } else if (MODE != MODE_SCOREMAP && tid < 32 + A_COLS) {
+    // phase-A validity masks: columns of word column wx whose flag matters (B <= x < xend, inside the tile + 1)
+    const int wx = tid - 32;
+    const int x = x0 - 4 + 4 * wx;
+    const int nlo = min(max(max(B, x0 - 1) - x, 0), 4), nhi = min(max(min(L.xend, x0 + TW + 1) - x, 0), 4);
+    s_vmcol[wx] = nlo < nhi ? ((0x01010101u << (8 * nlo)) & (0x01010101u >> (8 * (4 - nhi)))) * 0x1fu : 0u;
+  } else if (MODE != MODE_SCOREMAP && tid >= 96 && tid < 96 + A_GROUPS + 1) {
+    // ... and rows of row group g (B <= y < h-B, inside the score tile)
+    const int r0 = (tid - 96) * A_ROWS;
+    const int y = y0 - 1 + r0;
+    const int ilo = min(max(B - y, 0), A_ROWS), ihi = max(min(min(SC_H - r0, ys_end - y), A_ROWS), 0);
+    s_vmrow[tid - 96] = ilo < ihi ? (((1u << ihi) - 1u) & ~((1u << ilo) - 1u)) * 0x01010101u : 0u;
   }
 
   if (MODE == MODE_SCOREMAP) {
@@ -339,26 +364,44 @@ __global__ void __launch_bounds__(NT, PB_FRONT_MIN_CTAS) front_tile_kernel(const
     // a superset of the corners (phase B is exact), which buys the carry-tolerant compare of bytes_gt_loose.
     const int t = P.fast_t & 0xff;  // Fast.h:58 keeps the low byte
     const uint32_t listA_s = smem_u32(s_listA), nA_s = smem_u32(&s_nA);
-    const int xlo_rel = max(B, x0 - 1) - (x0 - 4), xhi_rel = min(L.xend, x0 + TW + 1) - (x0 - 4);
-    const int ylo_rel = B - (y0 - 1), yhi_rel = min(ys_end - (y0 - 1), SC_H);
+#if PB_TASK_LIST
+    const uint32_t nT_s = smem_u32(&s_nT);
+    uint2* const s_task = reinterpret_cast<uint2*>(s_listB);  // list B is dead until phase B
+#endif
     for (int task = tid; task < ((A_TASKS + 31) & ~31); task += NT) {
       // tasks A_TASKS.. of the last warp fall below the score tile (no valid row): they only take part in the scan
       const int g = task / A_COLS, wx = task - g * A_COLS;
       const int r0 = g * A_ROWS;
-      // columns / rows of the task whose flag matters here, relative to the task's first pixel (x0-4+4wx, y0-1+r0)
-      const int nlo = min(max(xlo_rel - 4 * wx, 0), 4), nhi = min(max(xhi_rel - 4 * wx, 0), 4);
-      const int ilo = min(max(ylo_rel - r0, 0), A_ROWS), ihi = min(max(yhi_rel - r0, 0), A_ROWS);
-      uint32_t acc = 0;  // bit 8k+i: pixel k of row r0+i is a candidate
-      if (nlo < nhi && ilo < ihi) {
-        const uint32_t colmask = (0x01010101u << (8 * nlo)) & (0x01010101u >> (8 * (4 - nhi)));
-        const uint32_t rowbits = ((1u << ihi) - 1u) & ~((1u << ilo) - 1u);
+      const uint32_t vm = s_vmcol[wx] & s_vmrow[g];  // bit 8k+i: the flag of pixel k, row r0+i matters here
+      uint32_t acc = 0;                              // bit 8k+i: that pixel is a candidate
+      if (vm) {
         const uint32_t* c = reinterpret_cast<const uint32_t*>(s_pix) + r0 * (PIX_W / 4) + (dxo >> 2) + 1 + wx;
-        acc = (t < 128 ? pretest_rows<true>(c, t) : pretest_rows<false>(c, t)) & (colmask * rowbits);
+        acc = (t < 128 ? pretest_rows<true>(c, t) : pretest_rows<false>(c, t)) & vm;
       }
-      // one list reservation per warp for all rows; a warp without candidates (30 % of them) skips it
-      constexpr int last = 31;
+#if PB_TASK_LIST
+      // only one task in eight has a candidate at all (but then ~8 of them): first compact the non-empty tasks
+      // (one ballot per warp round), then expand their bits into list A with dense lanes (phase A2)
+      const uint32_t nz = __ballot_sync(0xffffffffu, acc != 0u);
+      if (nz == 0u) continue;
+      const uint32_t tpos = warp_atom_shared_add(nT_s, (uint32_t)__popc(nz)) + __popc(nz & ((1u << lane) - 1u));
+      if (acc) s_task[tpos] = make_uint2(acc, (uint32_t)(r0 * SC_W + 4 * wx));
+    }
+    __syncthreads();
+
+    // ---- phase A2: candidate bits of the non-empty tasks -> list A -----------------------------------
+    const int nT = (int)s_nT;  // <= 256 tasks
+    for (int base = 0; base < nT; base += NT) {
+      if (base + (tid & ~31) >= nT) break;  // whole warps without a task
+      const int ti = base + tid;
+      const uint2 te = ti < nT ? s_task[ti] : make_uint2(0u, 0u);
+      uint32_t acc = te.x;
+      const int idx0 = (int)te.y;
+#else
+      if (__ballot_sync(0xffffffffu, acc != 0u) == 0u) continue;  // a warp without candidates (30 %) skips the rest
+      const int idx0 = r0 * SC_W + 4 * wx;
+#endif
+      // one list reservation per warp for all rows
       constexpr uint32_t amask = 0xffffffffu;
-      if (__ballot_sync(amask, acc != 0u) == 0u) continue;
       const uint32_t cnt = (uint32_t)__popc(acc);
       uint32_t incl = cnt;
 #pragma unroll
@@ -366,10 +409,8 @@ __global__ void __launch_bounds__(NT, PB_FRONT_MIN_CTAS) front_tile_kernel(const
         const uint32_t o = __shfl_up_sync(amask, incl, d);
         if (lane >= d) incl += o;
       }
-      uint32_t pos = 0;
-      if (lane == last) pos = atom_shared_add(nA_s, incl);
-      pos = __shfl_sync(amask, pos, last) + incl - cnt;
-      const int idx0 = r0 * SC_W + 4 * wx;
+      const uint32_t pos0 = warp_atom_shared_add(nA_s, __shfl_sync(0xffffffffu, incl, 31));
+      uint32_t pos = pos0 + incl - cnt;
       if (pos + cnt <= CAP_A) {
         // 20 predicated stores (a loop over the set bits runs with ~3 of 32 lanes busy); explicit shared
         // addresses: the compiler otherwise rebuilds the shared window base inside every predicated block
@@ -386,7 +427,7 @@ __global__ void __launch_bounds__(NT, PB_FRONT_MIN_CTAS) front_tile_kernel(const
           if (pos < CAP_A) {
             s_listA[pos] = (uint16_t)idx;
           } else {
-            test_candidate_inline(s_pix, s_score, idx, dxo, t, (x0 - 4 + 4 * wx + (b >> 3)) < xs_end, P.harris_t);
+            test_candidate_inline(s_pix, s_score, idx, dxo, t, (x0 - 4 + idx % SC_W) < xs_end, P.harris_t);
             s_dense = 1u;
           }
           ++pos;
