@@ -247,6 +247,9 @@ __device__ __noinline__ void test_candidate_inline(const uint8_t* s_pix, uint8_t
 #ifndef PB_TASK_LIST
 #define PB_TASK_LIST 1  // phase A compacts non-empty tasks before expanding their bits (0: expand per warp round)
 #endif
+#ifndef PB_WARP_TAIL
+#define PB_WARP_TAIL 1  // phases D/D2/E of a tile with <= 32 non-zero scores run in warp 0 alone
+#endif
 #ifndef PB_FRONT_MIN_CTAS
 #define PB_FRONT_MIN_CTAS 10  // 48 registers (32 B of spills); measured: 8 CTAs/SM +3 %, 9 +0.7 %, 11-12 +4 % (spills)
 #endif
@@ -495,6 +498,18 @@ __global__ void __launch_bounds__(NT, PB_FRONT_MIN_CTAS) front_tile_kernel(const
     atomicOr((lb == 0 ? s_bm : s_occ) + (slot >> 5), 1u << (slot & 31));
     return slot;
   };
+#if PB_WARP_TAIL
+  // A typical tile has a few dozen non-zero scores and keeps a handful of keypoints: one warp finishes it with
+  // warp-level synchronisation instead of three more block barriers; the other warps retire.
+  const bool warp_tail = !s_dense && s_nC <= 32u;
+  if (warp_tail && tid >= 32) return;
+#else
+  const bool warp_tail = false;
+#endif
+  auto tail_sync = [&]() {
+    if (warp_tail) __syncwarp();
+    else __syncthreads();
+  };
   if (!s_dense) {
     const int nC = (int)s_nC;
     for (int base = 0; base < nC; base += NT) {
@@ -528,7 +543,7 @@ __global__ void __launch_bounds__(NT, PB_FRONT_MIN_CTAS) front_tile_kernel(const
       }
     }
   }
-  __syncthreads();
+  tail_sync();
 
   const uint32_t* cells = s_cell;
   if (lb > 0) {
@@ -558,7 +573,7 @@ __global__ void __launch_bounds__(NT, PB_FRONT_MIN_CTAS) front_tile_kernel(const
         atomicOr(&s_bm[f >> 5], 1u << (f & 31));
       }
     }
-    __syncthreads();
+    tail_sync();
     cells = s_cell2;
   }
 

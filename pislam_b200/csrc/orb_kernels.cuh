@@ -29,6 +29,7 @@ struct OrbParams {
   RecordLayout rec;
   int row_off[MAX_LEVELS];
   int nframes;         // fused: frames in this launch; literal: 1
+  int frame0;          // fused TMA path: index of the launch's first frame in the tensor map (records/img point at it)
   int cap;             // fused: record capacity (slots per frame)
   const uint32_t* kp;  // literal: n keypoints with y relative to img
   int n;
@@ -204,6 +205,8 @@ __global__ void __launch_bounds__(ORB_WARPS * 32) orb_kernel(const __grid_consta
 // The pattern is evaluated straight out of the TMA buffer (table offsets for a 48-byte pitch + ob).
 // --------------------------------------------------------------------------------------------------
 constexpr int OT_W = 48, OT_H = 31, OT_BYTES = OT_W * OT_H, OT_STRIDE = 1536;
+constexpr int ORB_FRAMES_PER_THREAD = 4;
+constexpr int ORB_MAX_FRAMES = ORB_WARPS * 32 * ORB_FRAMES_PER_THREAD;  // frames per launch (the host splits larger batches)
 
 struct OrbKp {
   int frame, i, x, y;
@@ -215,6 +218,7 @@ __global__ void __launch_bounds__(ORB_WARPS * 32) orb_tma_kernel(const __grid_co
   __shared__ __align__(8) uint64_t s_bar[ORB_WARPS][2];
   __shared__ uint32_t s_wx[16 * 9], s_w1[16 * 9];
   __shared__ uint16_t s_recpe[256];
+  __shared__ uint32_t s_start[ORB_MAX_FRAMES + 1], s_wsum[ORB_WARPS];
   build_disc_tables(s_wx, s_w1);
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_recpe[i] = (uint16_t)recpe_mantissa((uint32_t)i);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -224,41 +228,70 @@ __global__ void __launch_bounds__(ORB_WARPS * 32) orb_tma_kernel(const __grid_co
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  // this warp visits slots gw, gw + nwarps, ... of the (frame, slot-in-record) space; the position is kept
-  // as (frame, i) and advanced by (nwarps / cap, nwarps % cap) so that no division sits in the loop
-  const int nwarps = (int)gridDim.x * ORB_WARPS;
-  const int dq = nwarps / P.cap, dr = nwarps % P.cap;
-  const int gw = (int)blockIdx.x * ORB_WARPS + warp;
-  int frame = gw / P.cap - dq, idx = gw % P.cap - dr;
-  if (idx < 0) {
-    idx += P.cap;
-    --frame;
+  // Keypoints are numbered across the launch's frames (exclusive scan of the record counts, once per CTA); CTA c
+  // owns the contiguous range [K c / G, K (c+1) / G) and its warps interleave inside it.  No empty record slot is
+  // ever visited, a warp stays in one frame (and its neighbourhood of the image) for a long time, and every CTA
+  // gets the same number of keypoints.
+  {
+    const int f0 = (int)threadIdx.x * ORB_FRAMES_PER_THREAD;
+    uint32_t c[ORB_FRAMES_PER_THREAD], sum = 0;
+#pragma unroll
+    for (int j = 0; j < ORB_FRAMES_PER_THREAD; ++j) {
+      c[j] = f0 + j < P.nframes
+                 ? min(__ldg(reinterpret_cast<const uint32_t*>(P.records + (size_t)(f0 + j) * P.rec.bytes)), (uint32_t)P.cap)
+                 : 0u;
+      sum += c[j];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    uint32_t run = incl - sum;
+    for (int w = 0; w < warp; ++w) run += s_wsum[w];
+    if (threadIdx.x == 0) s_start[0] = 0u;
+#pragma unroll
+    for (int j = 0; j < ORB_FRAMES_PER_THREAD; ++j) {
+      run += c[j];
+      if (f0 + j < P.nframes) s_start[f0 + j + 1] = run;
+    }
+  }
+  __syncthreads();
+  const uint32_t K = s_start[P.nframes];
+  const uint32_t k_end = (uint32_t)((unsigned long long)K * (blockIdx.x + 1) / gridDim.x);
+  uint32_t kk = (uint32_t)((unsigned long long)K * blockIdx.x / gridDim.x) + (uint32_t)warp;
+  int frame = 0;
+  if (kk < k_end) {  // frame of the warp's first keypoint: the last f with s_start[f] <= kk
+    int lo = 0, hi = P.nframes;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_start[mid] <= kk) lo = mid;
+      else hi = mid;
+    }
+    frame = lo;
   }
 
-  // next occupied slot of this warp's stride (all lanes compute the same values)
+  // this warp's next keypoint (all lanes compute the same values)
   auto advance = [&](OrbKp& k) -> bool {
-    for (;;) {
-      frame += dq;
-      idx += dr;
-      if (idx >= P.cap) {
-        idx -= P.cap;
-        ++frame;
-      }
-      if (frame >= P.nframes) return false;
-      const uint8_t* rec = P.records + (size_t)frame * P.rec.bytes;
-      if (idx >= (int)__ldg(reinterpret_cast<const uint32_t*>(rec))) continue;
-      const uint32_t e = __ldg(reinterpret_cast<const uint32_t*>(rec + P.rec.kp_off) + idx);
-      k.frame = frame;
-      k.i = idx;
-      k.x = (int)decode_x(e);
-      k.y = (int)decode_y(e) + P.row_off[__ldg(rec + P.rec.level_off + idx)];
-      return true;
-    }
+    if (kk >= k_end) return false;
+    while (kk >= s_start[frame + 1]) ++frame;
+    const int idx = (int)(kk - s_start[frame]);
+    kk += ORB_WARPS;
+    const uint8_t* rec = P.records + (size_t)frame * P.rec.bytes;
+    const uint32_t e = __ldg(reinterpret_cast<const uint32_t*>(rec + P.rec.kp_off) + idx);
+    k.frame = frame;
+    k.i = idx;
+    k.x = (int)decode_x(e);
+    k.y = (int)decode_y(e) + P.row_off[__ldg(rec + P.rec.level_off + idx)];
+    return true;
   };
   auto issue = [&](const OrbKp& k, int b) {
     if (lane == 0) {
       mbar_expect_tx(&s_bar[warp][b], OT_BYTES);
-      tma_load_3d(s_buf[warp][b], &tmap, (k.x - 15) & ~15, k.y - 15, k.frame, &s_bar[warp][b]);
+      tma_load_3d(s_buf[warp][b], &tmap, (k.x - 15) & ~15, k.y - 15, P.frame0 + k.frame, &s_bar[warp][b]);
     }
   };
 

@@ -151,6 +151,7 @@ struct pislam_ctx {
   cudaStream_t stream = nullptr;
   long launches = 0;
   int num_sms = 148;
+  int orb_tma_ctas_per_sm = 0;  // occupancy of orb_tma_kernel (queried once)
   bool use_tma = true;
   EncodeTiledFn encode = nullptr;
   uint32_t* d_brief = nullptr;    // pattern offsets for the 36-byte patch pitch
@@ -410,8 +411,23 @@ int enqueue_extract(pislam_ctx* c, const uint8_t* d_stacks, size_t frame_stride,
                          make_tensor_map(c, &omap, d_stacks, d->vstep, g.rows, nframes, frame_stride, OT_W, OT_H) == PISLAM_OK;
     span_begin(c, 2);
     if (orb_tma) {
-      const dim3 grid((unsigned)std::min<long long>(want, (long long)c->num_sms * 8));
-      orb_tma_kernel<<<grid, ORB_WARPS * 32, 0, c->stream>>>(Q, omap);
+      // every CTA of the grid is resident (the kernel splits the keypoints evenly over gridDim.x CTAs)
+      if (c->orb_tma_ctas_per_sm == 0) {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, orb_tma_kernel, ORB_WARPS * 32, 0) != cudaSuccess || occ < 1)
+          occ = 1;
+        c->orb_tma_ctas_per_sm = occ;
+      }
+      for (int f0 = 0; f0 < nframes; f0 += ORB_MAX_FRAMES) {
+        OrbParams R = Q;
+        R.nframes = std::min(ORB_MAX_FRAMES, nframes - f0);
+        R.frame0 = f0;
+        R.records = d_records + (size_t)f0 * Q.rec.bytes;
+        const long long slots = ((long long)R.nframes * cap + ORB_WARPS - 1) / ORB_WARPS;
+        const dim3 grid((unsigned)std::min<long long>(slots, (long long)c->num_sms * c->orb_tma_ctas_per_sm));
+        orb_tma_kernel<<<grid, ORB_WARPS * 32, 0, c->stream>>>(R, omap);
+        if (f0 + ORB_MAX_FRAMES < nframes) ++c->launches;
+      }
     } else {
       const dim3 grid((unsigned)std::min<long long>(want, (long long)c->num_sms * 8));
       orb_kernel<1><<<grid, ORB_WARPS * 32, 0, c->stream>>>(Q);
