@@ -259,6 +259,32 @@ def test_fused_batch_and_capacity(ctx, oracle):
     assert_same(kp, res[0][0], "after overflow")
 
 
+def test_fused_batch_beyond_one_descriptor_launch(ctx, oracle):
+    """1030 small frames: orb_tma_kernel numbers the keypoints of at most 1024 frames per launch, so this batch
+    takes two descriptor launches (second one with a frame offset); all-black frames in between have no keypoints
+    and must be skipped by the flat numbering."""
+    lay = pyramid_layout(160, 96, nlevels=2)
+    rng = np.random.Generator(np.random.PCG64(21))
+    src = [synthetic_stack(lay, 40), noise_stack(lay, 41), np.zeros((lay.rows, lay.vstep), np.uint8),
+           synthetic_stack(lay, 42), np.zeros((lay.rows, lay.vstep), np.uint8), noise_stack(lay, 43)]
+    want = [oracle_pyramid(oracle, s_, lay, fast_threshold=30, harris_threshold=1 << 13, cap=1 << 14) for s_ in src]
+    assert any(len(w[0]) == 0 for w in want) and any(len(w[0]) > 50 for w in want)
+    nf = 1030
+    which = rng.integers(0, len(src), size=nf)
+    which[1022:1028] = [1, 2, 3, 0, 5, 4]  # both sides of the launch boundary
+    stacks = np.stack([src[k] for k in which])
+    d = api.make_desc(lay, fast_threshold=30, harris_threshold=1 << 13)
+    cap = max(len(w[0]) for w in want) + 8
+    res = ctx.extract_batch(stacks, d, cap=cap)
+    assert len(res) == nf
+    for f in range(nf):
+        okp, olv, odesc = want[which[f]]
+        kp, lv, desc, level_start, n_total = res[f]
+        assert n_total == len(okp), "frame %d" % f
+        assert_same(kp, okp, "frame %d keypoints" % f)
+        assert_same(desc, odesc, "frame %d descriptors" % f)
+
+
 def test_fused_keypoints_only_and_words(ctx, oracle):
     stack = synthetic_stack(VGA, 2)
     for words in (0, 1, 4, 8):
