@@ -499,7 +499,13 @@ int pislam_b200_create(pislam_ctx** out, int device, size_t max_stack_bytes, int
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { st = -(int)e; break; }
     if ((e = cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking)) != cudaSuccess) { st = -(int)e; break; }
     if ((e = cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking)) != cudaSuccess) { st = -(int)e; break; }
-    if ((e = cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking)) != cudaSuccess) { st = -(int)e; break; }
+    {
+      // the all-gather of batch k runs under the kernels of batch k+1, whose grids keep every CTA slot busy:
+      // the gather's CTAs have to win the slots that free up, so its stream gets the highest priority
+      int prio_lo = 0, prio_hi = 0;
+      if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) prio_hi = 0;
+      if ((e = cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) { st = -(int)e; break; }
+    }
     if ((e = cudaEventCreateWithFlags(&c->ev_extract, cudaEventDisableTiming)) != cudaSuccess) { st = -(int)e; break; }
     for (int i = 0; i < 2 && st == PISLAM_OK; ++i)
       if ((e = cudaEventCreateWithFlags(&c->gathers[i].done, cudaEventDisableTiming)) != cudaSuccess) st = -(int)e;
