@@ -172,6 +172,27 @@ int pislam_b200_join(pislam_ctx* ctx);
  * bytes) this rank has already filled, e.g. with pislam_b200_extract_batch on device records. */
 int pislam_b200_allgather(pislam_ctx* ctx, void* d_all, size_t bytes_per_rank);
 
+/* ---- descriptor matching --------------------------------------------------
+ * NOT a replacement of reference code: the reference never released its matcher (README.md:125-139
+ * mentions flann-based matching with table-driven bit counts and a demo tracing "best matches within a
+ * 20 pixel radius").  Definition (restated in numpy in tests/oracle_lib.py:match_hamming):
+ *   distance(q, t) = popcount of the XOR of the `words` descriptor words;
+ *   candidates of query q: every train descriptor (radius <= 0), or the train keypoints on the SAME pyramid
+ *   level with (xq-xt)^2 + (yq-yt)^2 <= radius^2 in level-local pixels (radius > 0);
+ *   result [3] per query: index of the closest candidate (smallest index wins ties; -1 if none), its
+ *   distance, and the distance of the runner-up (a tie with the best counts), PISLAM_MATCH_NONE when absent.
+ * kp/level may be null when radius <= 0.  Host pointers; blocking. */
+#define PISLAM_MATCH_NONE 0x7fffffff
+int pislam_b200_match_hamming(pislam_ctx* ctx, const uint32_t* q_desc, const uint32_t* q_kp, const uint8_t* q_level,
+                              int nq, const uint32_t* t_desc, const uint32_t* t_kp, const uint8_t* t_level, int nt,
+                              int words, int radius, int32_t* matches /* [nq][3] */);
+/* The same for frame pairs of a batch of records (pislam_b200_extract_batch output, host or device):
+ * pairs[2*p] = query frame, pairs[2*p+1] = train frame (host array); matches[p][cap][3] (host or device,
+ * rows >= n of the query frame are left untouched).  One launch for all pairs; blocking only when a buffer
+ * is on the host. */
+int pislam_b200_match_records(pislam_ctx* ctx, const uint8_t* records, int nframes, int cap, int words,
+                              const int32_t* pairs, int npairs, int radius, int32_t* matches);
+
 /* ---- introspection for tests ----------------------------------------------------------------- */
 /* The rotated + clamped rBRIEF pattern the device uses, int8[30][256][4] = (x0,y0,x1,y1)
  * (reference Brief.h:28-50). */

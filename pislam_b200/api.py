@@ -87,6 +87,10 @@ _SIGNATURES = {
                                                 C.POINTER(PyramidDesc), C.c_int, C.c_void_p]),
     "pislam_b200_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "pislam_b200_join": (C.c_int, [C.c_void_p]),
+    "pislam_b200_match_hamming": (C.c_int, [C.c_void_p, _u32p, _u32p, _u8p, C.c_int, _u32p, _u32p, _u8p, C.c_int,
+                                            C.c_int, C.c_int, _i32p]),
+    "pislam_b200_match_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int,
+                                            C.c_int, C.c_void_p]),
     "pislam_b200_brief_table": (C.c_int, [C.POINTER(C.c_int8)]),
 }
 
@@ -316,6 +320,32 @@ class Context:
         _check_img(img)
         _check_img(out, "out")
         self._ok(self.lib.pislam_b200_bilinear13_16(self._h, _p(img, _u8p), _p(out, _u8p), img.shape[1], width, height))
+
+    # ---- descriptor matching (not in the reference, definition in include/pislam_b200.h) ----
+    def match_hamming(self, q_desc, t_desc, q_kp=None, q_level=None, t_kp=None, t_level=None, radius=0):
+        """Best / second-best Hamming match of every query descriptor -> int32 [nq][3] = (index, dist, second)."""
+        q_desc, t_desc = np.ascontiguousarray(q_desc, np.uint32), np.ascontiguousarray(t_desc, np.uint32)
+        words = next((int(a.size // len(a)) for a in (q_desc, t_desc) if len(a)), 8)
+        q_desc, t_desc = q_desc.reshape(len(q_desc), words), t_desc.reshape(len(t_desc), words)
+        out = np.zeros((len(q_desc), 3), np.int32)
+        arrs = []
+        for a, t in ((q_kp, np.uint32), (q_level, np.uint8), (t_kp, np.uint32), (t_level, np.uint8)):
+            arrs.append(None if a is None else np.ascontiguousarray(a, t))
+        ptr = lambda a, t: None if a is None or a.size == 0 else _p(a, t)  # noqa: E731
+        self._ok(self.lib.pislam_b200_match_hamming(
+            self._h, ptr(q_desc, _u32p), ptr(arrs[0], _u32p), ptr(arrs[1], _u8p), len(q_desc),
+            ptr(t_desc, _u32p), ptr(arrs[2], _u32p), ptr(arrs[3], _u8p), len(t_desc), words, radius,
+            _p(out, _i32p) if out.size else None))
+        return out
+
+    def match_records(self, records, nframes, cap, words, pairs, radius=0):
+        """Matches for frame pairs of a host batch of records -> int32 [npairs][cap][3] (rows >= n stay -2)."""
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        out = np.full((len(pairs), cap, 3), -2, np.int32)
+        self._ok(self.lib.pislam_b200_match_records(self._h, records.ctypes.data, nframes, cap, words,
+                                                    _p(pairs, _i32p) if pairs.size else None, len(pairs), radius,
+                                                    out.ctypes.data))
+        return out
 
     # ---- fused whole-pyramid path (the caller loop of demo/demo.cpp:77-101) -------------------------
     def extract_pyramid(self, stack, desc, cap=4096):

@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libpislam_b200.so")
 SOURCES = ["pislam_b200.cu"]
-HEADERS = ["device_ops.cuh", "front_kernels.cuh", "orb_kernels.cuh", "pyramid_kernels.cuh", "brief_pattern.h",
+HEADERS = ["device_ops.cuh", "front_kernels.cuh", "orb_kernels.cuh", "pyramid_kernels.cuh", "match_kernels.cuh", "brief_pattern.h",
            os.path.join("..", "..", "include", "pislam_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared"]

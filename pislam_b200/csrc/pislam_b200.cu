@@ -21,6 +21,7 @@
 #include "brief_pattern.h"
 #include "front_kernels.cuh"
 #include "orb_kernels.cuh"
+#include "match_kernels.cuh"
 #include "pyramid_kernels.cuh"
 
 using namespace pb;
@@ -1118,6 +1119,92 @@ int pislam_b200_allgather(pislam_ctx* c, void* d_all, size_t bytes_per_rank) {
   const uint8_t* mine = static_cast<const uint8_t*>(d_all) + bytes_per_rank * (size_t)c->rank;
   const int r = g_nccl.AllGather(mine, d_all, bytes_per_rank, /*ncclInt8*/ 0, c->comm, c->stream);
   if (r != 0) return PISLAM_ERR_NCCL - r;
+  return PISLAM_OK;
+}
+
+// ---- descriptor matching (definition in include/pislam_b200.h) ------------------------
+int pislam_b200_match_hamming(pislam_ctx* c, const uint32_t* q_desc, const uint32_t* q_kp, const uint8_t* q_level,
+                              int nq, const uint32_t* t_desc, const uint32_t* t_kp, const uint8_t* t_level, int nt,
+                              int words, int radius, int32_t* matches) {
+  if (!c || nq < 0 || nt < 0 || words < 1 || words > 8 || (nq && (!q_desc || !matches)) || (nt && !t_desc))
+    return PISLAM_ERR_INVALID_ARG;
+  if (radius > 0 && ((nq && (!q_kp || !q_level)) || (nt && (!t_kp || !t_level)))) return PISLAM_ERR_INVALID_ARG;
+  if (radius > 5792) return PISLAM_ERR_INVALID_ARG;  // radius^2 and the 12-bit coordinate differences stay in int32
+  if (nq == 0) return PISLAM_OK;
+  CKS(set_device(c));
+  // one staging buffer: query desc | train desc | query kp | train kp | query level | train level | out
+  const size_t qd = (size_t)nq * words * 4, td = (size_t)nt * words * 4, qk = (size_t)nq * 4, tk = (size_t)nt * 4;
+  const size_t lv_q = ((size_t)nq + 3) & ~(size_t)3, lv_t = ((size_t)nt + 3) & ~(size_t)3, ob = (size_t)nq * 12;
+  CK(c->aux0.reserve(qd + td + qk + tk + lv_q + lv_t + ob + 64, false, c->stream));
+  uint8_t* base = c->aux0.as<uint8_t>();
+  uint8_t *d_qd = base, *d_td = d_qd + qd, *d_qk = d_td + td, *d_tk = d_qk + qk, *d_ql = d_tk + tk, *d_tl = d_ql + lv_q,
+          *d_out = d_tl + lv_t;
+  CK(cudaMemcpyAsync(d_qd, q_desc, qd, cudaMemcpyHostToDevice, c->stream));
+  if (nt) CK(cudaMemcpyAsync(d_td, t_desc, td, cudaMemcpyHostToDevice, c->stream));
+  if (radius > 0) {
+    CK(cudaMemcpyAsync(d_qk, q_kp, qk, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_ql, q_level, (size_t)nq, cudaMemcpyHostToDevice, c->stream));
+    if (nt) {
+      CK(cudaMemcpyAsync(d_tk, t_kp, tk, cudaMemcpyHostToDevice, c->stream));
+      CK(cudaMemcpyAsync(d_tl, t_level, (size_t)nt, cudaMemcpyHostToDevice, c->stream));
+    }
+  }
+  MatchParams M;
+  memset(&M, 0, sizeof(M));
+  M.words = words;
+  M.radius = radius;
+  M.q_desc = reinterpret_cast<const uint32_t*>(d_qd);
+  M.q_kp = reinterpret_cast<const uint32_t*>(d_qk);
+  M.q_level = d_ql;
+  M.nq = nq;
+  M.t_desc = reinterpret_cast<const uint32_t*>(d_td);
+  M.t_kp = reinterpret_cast<const uint32_t*>(d_tk);
+  M.t_level = d_tl;
+  M.nt = nt;
+  M.out = reinterpret_cast<int32_t*>(d_out);
+  match_kernel<0><<<dim3((nq + MATCH_NT - 1) / MATCH_NT, 1), MATCH_NT, 0, c->stream>>>(M);
+  CKS(check_launch(c));
+  CK(cudaMemcpyAsync(matches, d_out, ob, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return PISLAM_OK;
+}
+
+int pislam_b200_match_records(pislam_ctx* c, const uint8_t* records, int nframes, int cap, int words,
+                              const int32_t* pairs, int npairs, int radius, int32_t* matches) {
+  if (!c || !records || nframes < 1 || cap < 1 || words < 1 || words > 8 || npairs < 0 || (npairs && (!pairs || !matches)))
+    return PISLAM_ERR_INVALID_ARG;
+  if (radius > 5792 || npairs > 65535) return PISLAM_ERR_INVALID_ARG;
+  for (int i = 0; i < 2 * npairs; ++i)
+    if (pairs[i] < 0 || pairs[i] >= nframes) return PISLAM_ERR_INVALID_ARG;
+  if (npairs == 0) return PISLAM_OK;
+  CKS(set_device(c));
+  const RecordLayout rec = RecordLayout::make(cap, words);
+  const bool rec_on_host = !is_device_ptr(records), out_on_host = !is_device_ptr(matches);
+  const uint8_t* d_rec = records;
+  if (rec_on_host) {
+    CK(c->records.reserve((size_t)nframes * rec.bytes, false, c->stream));
+    CK(cudaMemcpyAsync(c->records.p, records, (size_t)nframes * rec.bytes, cudaMemcpyHostToDevice, c->stream));
+    d_rec = c->records.as<uint8_t>();
+  }
+  const size_t out_bytes = (size_t)npairs * cap * 12, pair_bytes = (size_t)npairs * 8;
+  CK(c->aux1.reserve(pair_bytes + (out_on_host ? out_bytes : 0) + 64, false, c->stream));
+  int32_t* d_pairs = c->aux1.as<int32_t>();
+  int32_t* d_out = out_on_host ? reinterpret_cast<int32_t*>(c->aux1.as<uint8_t>() + ((pair_bytes + 15) & ~(size_t)15)) : matches;
+  CK(cudaMemcpyAsync(d_pairs, pairs, pair_bytes, cudaMemcpyHostToDevice, c->stream));
+  if (out_on_host) CK(cudaMemcpyAsync(d_out, matches, out_bytes, cudaMemcpyHostToDevice, c->stream));  // untouched rows stay
+  MatchParams M;
+  memset(&M, 0, sizeof(M));
+  M.words = words;
+  M.radius = radius;
+  M.records = d_rec;
+  M.rec = rec;
+  M.cap = cap;
+  M.pairs = d_pairs;
+  M.out = d_out;
+  match_kernel<1><<<dim3((cap + MATCH_NT - 1) / MATCH_NT, npairs), MATCH_NT, 0, c->stream>>>(M);
+  CKS(check_launch(c));
+  if (out_on_host) CK(cudaMemcpyAsync(matches, d_out, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+  if (out_on_host || rec_on_host) CK(cudaStreamSynchronize(c->stream));
   return PISLAM_OK;
 }
 
