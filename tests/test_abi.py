@@ -74,6 +74,10 @@ SIGNATURE_TU = r"""
 #include "pislam/Util.h"
 #include "pislam/Gaussian.h"
 #include "pislam/Bilinear.h"
+#include "pislam/Match.h"  // our addition (SURVEY.md 8f N2): must at least instantiate
+std::vector<pislam::Match> (*p_match)(const std::vector<uint32_t>&, const std::vector<uint32_t>&, int,
+                                     const std::vector<uint32_t>*, const std::vector<uint8_t>*,
+                                     const std::vector<uint32_t>*, const std::vector<uint8_t>*) = &pislam::matchHamming<8>;
 // exact function types of the reference's templates (vstep 640, border 16, words 8)
 typedef uint8_t Row[640];
 void (*p_detect)(const int, const int, Row*, Row*, int) = &pislam::fastDetect<640, 16>;
