@@ -207,6 +207,20 @@ def test_fused_noise_and_thresholds(ctx, oracle):
         assert_same(desc, odesc, "noise descriptors")
 
 
+def test_fused_small_thresholds_on_noise(ctx, oracle):
+    """FAST thresholds 0..5 and 126/127 on uniform noise: ties |p-c| == t next to large differences are everywhere,
+    which is where the carry-tolerant pre-test of phase A admits false candidates (and must lose no corner)."""
+    lay = pyramid_layout(256, 160, nlevels=2)
+    stack = noise_stack(lay, 17)
+    for ft in (0, 1, 2, 5, 126, 127):
+        d = api.make_desc(lay, fast_threshold=ft, harris_threshold=1 << 14, log_bucket=0, bucket_limit=5)
+        kp, lv, desc = ctx.extract_pyramid(stack, d, cap=1 << 16)
+        okp, olv, odesc = oracle_pyramid(oracle, stack, lay, fast_threshold=ft, harris_threshold=1 << 14, cap=1 << 16)
+        assert len(okp) > 0 or ft >= 126
+        assert_same(kp, okp, "noise ft=%d keypoints" % ft)
+        assert_same(desc, odesc, "noise ft=%d descriptors" % ft)
+
+
 def test_fused_ragged_geometries(ctx, oracle):
     """Odd / tiny / non-multiple-of-16 levels, a vstep that is not a multiple of 16 (plain-load staging),
     levels with no interior, border 16 and larger."""
