@@ -1,6 +1,6 @@
 // Detector front-end kernels (sm_100a): FAST-9 -> Harris code -> 3x3 non-max -> ordered keypoint list.
 //
-//   front_tile_kernel   one CTA per 128x32 tile of one pyramid level of one frame; the whole batch
+//   front_tile_kernel   one CTA per 128x64 tile of one pyramid level of one frame; the whole batch
 //                       (all levels of all frames) is ONE launch over a tile table.
 //                         MODE_TMA       pixel tile (+halo) staged by one 3-D TMA box load
 //                         MODE_LDG       same, staged with plain loads (vstep not a multiple of 16)
@@ -23,7 +23,10 @@
 namespace pb {
 
 constexpr int TW = 128;             // tile width  (output pixels)
-constexpr int TH = 32;              // tile height (output pixels)
+#ifndef PB_TH
+#define PB_TH 64  // tile height: 64 (measured: 0.310 ms per 256 VGA frames) or 32 (0.347 ms)
+#endif
+constexpr int TH = PB_TH;           // tile height (output pixels)
 constexpr int NT = 128;             // threads per CTA
 constexpr int PIX_W = TW + 32;      // staged pixels: origin (x0-8-dxo, y0-4); a TMA box must start on a
                                     // 16-byte boundary of the row, so dxo = (x0-8) & 15 there, 0 otherwise
@@ -33,7 +36,7 @@ constexpr int SC_H = TH + 2;
 constexpr int SC_WW = SC_W / 4;     // score-tile words per row
 constexpr int NWORD = SC_WW * SC_H; // FAST work items (4 pixels each)
 constexpr int CELLS_X = TW / 2, CELLS_Y = TH / 2;
-constexpr int NCELL = CELLS_X * CELLS_Y;  // 1024 = 4 per thread
+constexpr int NCELL = CELLS_X * CELLS_Y;  // 2048 (TH 64) / 1024 (TH 32) 2x2 cells per tile
 constexpr int MAX_LEVELS = 16;
 
 enum { MODE_TMA = 0, MODE_LDG = 1, MODE_SCOREMAP = 2 };
@@ -216,17 +219,19 @@ __device__ __forceinline__ bool nms_survives(const uint8_t* q, int pitch) {
 // -> bitmap over output slots -> E (rank by popcount prefix = the reference's order).
 constexpr int A_COLS = SC_WW;                       // 34 word columns
 constexpr int A_ROWS = 5;                           // rows per phase-A thread
-constexpr int A_GROUPS = (SC_H + A_ROWS - 1) / A_ROWS;  // 7
-constexpr int A_TASKS = A_COLS * A_GROUPS;          // 238 (word column, row group) tasks
-static_assert(A_GROUPS * A_ROWS + 6 <= PIX_H + 1, "phase A rows stay inside the staged tile");
+constexpr int A_GROUPS = (SC_H + A_ROWS - 1) / A_ROWS;  // 14 (TH 64) / 7 (TH 32)
+constexpr int A_TASKS = A_COLS * A_GROUPS;          // 476 / 238 (word column, row group) tasks
+// rows the last (partly invalid) row group of phase A reads beyond the staged tile: kept inside s_pix by padding
+constexpr int PIX_PAD_ROWS = A_GROUPS * A_ROWS + 6 > PIX_H ? A_GROUPS * A_ROWS + 6 - PIX_H : 0;
+static_assert(NCELL % 1024 == 0 && NCELL / 32 <= 64, "phase E: one or two bitmap words per lane of one warp");
 static_assert(A_ROWS == 5, "pretest_rows and the 5-bit row mask are written for 5 rows per task");
 
 // Work-list capacities.  Natural images need ~130 candidates / ~50 corners per tile; the lists are sized for
 // 15x / 20x that and anything beyond is handled EXACTLY but slowly (inline, then a dense non-max scan), so that
 // adversarial tiles (noise, checkerboards) stay bit-exact while the common case keeps 18 KB of shared memory.
-constexpr int CAP_A = 2048;  // list A: FAST candidates, later non-zero scores (also hosts the 4 KB slot array)
-constexpr int CAP_B = 1024;  // list B: FAST corners, later NMS survivors (at most one per cell = 1024)
-static_assert(CAP_A * 2 >= NCELL * 4 && CAP_B >= NCELL, "list A hosts s_cell2; list B holds one survivor per cell");
+constexpr int CAP_A = 2048;       // list A: FAST candidates, later non-zero scores (at most one per corner <= CAP_B)
+constexpr int CAP_B = NCELL;      // list B: FAST corners, later NMS survivors (at most one per cell)
+static_assert(CAP_A >= CAP_B && CAP_B >= NCELL, "list A holds one entry per corner of list B; list B one survivor per cell");
 static_assert(CAP_B * 2 >= ((A_TASKS + 31) & ~31) * 8, "list B hosts the phase-A task list (8 bytes per task)");
 
 // Slow path of a corner that did not fit into list B: score it in place (rarely executed, kept out of line)
@@ -250,13 +255,20 @@ __device__ __noinline__ void test_candidate_inline(const uint8_t* s_pix, uint8_t
 #ifndef PB_WARP_TAIL
 #define PB_WARP_TAIL 1  // phases D/D2/E of a tile with <= 32 non-zero scores run in warp 0 alone
 #endif
+#ifndef PB_TAIL_MAX
+#define PB_TAIL_MAX 32  // non-zero scores up to which one warp runs the tail
+#endif
 #ifndef PB_FRONT_MIN_CTAS
+#if PB_TH == 64
+#define PB_FRONT_MIN_CTAS 7  // 30 KB of shared memory per CTA, 72 registers; 6 CTAs/SM (34 KB lists) measured +7 %
+#else
 #define PB_FRONT_MIN_CTAS 10  // 48 registers (32 B of spills); measured: 8 CTAs/SM +3 %, 9 +0.7 %, 11-12 +4 % (spills)
+#endif
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(NT, PB_FRONT_MIN_CTAS) front_tile_kernel(const __grid_constant__ FrontParams P,
                                                         const __grid_constant__ CUtensorMap tmap) {
-  __shared__ __align__(128) uint8_t s_pix[PIX_H * PIX_W];
+  __shared__ __align__(128) uint8_t s_pix[(PIX_H + PIX_PAD_ROWS) * PIX_W];
   __shared__ __align__(16) uint8_t s_score[SC_H * SC_W];
   __shared__ __align__(16) uint16_t s_listA[CAP_A];  // FAST candidates (A->B), then non-zero scores (C->D)
   __shared__ __align__(8) uint16_t s_listB[CAP_B];   // FAST corners (B->C), then NMS survivors (D->D2); hosts the
@@ -266,10 +278,10 @@ __global__ void __launch_bounds__(NT, PB_FRONT_MIN_CTAS) front_tile_kernel(const
   __shared__ uint32_t s_nA, s_nB, s_nC, s_nS, s_nT;
   __shared__ uint32_t s_dense;  // a list overflowed: scores were written in place, phase D scans every cell
   __shared__ __align__(8) uint64_t s_bar;
-  // the slot arrays reuse buffers that are dead by then: the pixels after phase C, list A after phase D
-  static_assert(sizeof(s_pix) >= NCELL * 4 && sizeof(s_listA) >= NCELL * 4, "slot arrays alias s_pix / s_listA");
+  // the slot arrays reuse buffers that are dead by then: the pixels after phase C, the scores after phase D
+  static_assert(sizeof(s_pix) >= NCELL * 4 && sizeof(s_score) >= NCELL * 4, "slot arrays alias s_pix / s_score");
   uint32_t* const s_cell = reinterpret_cast<uint32_t*>(s_pix);
-  uint32_t* const s_cell2 = reinterpret_cast<uint32_t*>(s_listA);
+  uint32_t* const s_cell2 = reinterpret_cast<uint32_t*>(s_score);
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -304,19 +316,21 @@ __global__ void __launch_bounds__(NT, PB_FRONT_MIN_CTAS) front_tile_kernel(const
   if (tid < NCELL / 32) {
     s_bm[tid] = 0u;
     s_occ[tid] = 0u;
-  } else if (MODE != MODE_SCOREMAP && tid < 32 + A_COLS) {
+  } else if (MODE != MODE_SCOREMAP && tid < NCELL / 32 + A_COLS) {
     // phase-A validity masks: columns of word column wx whose flag matters (B <= x < xend, inside the tile + 1)
-    const int wx = tid - 32;
+    const int wx = tid - NCELL / 32;
     const int x = x0 - 4 + 4 * wx;
     const int nlo = min(max(max(B, x0 - 1) - x, 0), 4), nhi = min(max(min(L.xend, x0 + TW + 1) - x, 0), 4);
     s_vmcol[wx] = nlo < nhi ? ((0x01010101u << (8 * nlo)) & (0x01010101u >> (8 * (4 - nhi)))) * 0x1fu : 0u;
-  } else if (MODE != MODE_SCOREMAP && tid >= 96 && tid < 96 + A_GROUPS + 1) {
+  } else if (MODE != MODE_SCOREMAP && tid < NCELL / 32 + A_COLS + A_GROUPS + 1) {
     // ... and rows of row group g (B <= y < h-B, inside the score tile)
-    const int r0 = (tid - 96) * A_ROWS;
+    const int g = tid - (NCELL / 32 + A_COLS);
+    const int r0 = g * A_ROWS;
     const int y = y0 - 1 + r0;
     const int ilo = min(max(B - y, 0), A_ROWS), ihi = max(min(min(SC_H - r0, ys_end - y), A_ROWS), 0);
-    s_vmrow[tid - 96] = ilo < ihi ? (((1u << ihi) - 1u) & ~((1u << ilo) - 1u)) * 0x01010101u : 0u;
+    s_vmrow[g] = ilo < ihi ? (((1u << ihi) - 1u) & ~((1u << ilo) - 1u)) * 0x01010101u : 0u;
   }
+  static_assert(NCELL / 32 + A_COLS + A_GROUPS + 1 <= NT, "set-up roles fit the CTA");
 
   if (MODE == MODE_SCOREMAP) {
     __syncthreads();
@@ -501,18 +515,19 @@ __global__ void __launch_bounds__(NT, PB_FRONT_MIN_CTAS) front_tile_kernel(const
 #if PB_WARP_TAIL
   // A typical tile has a few dozen non-zero scores and keeps a handful of keypoints: one warp finishes it with
   // warp-level synchronisation instead of three more block barriers; the other warps retire.
-  const bool warp_tail = !s_dense && s_nC <= 32u;
+  const bool warp_tail = !s_dense && s_nC <= (unsigned)PB_TAIL_MAX;
   if (warp_tail && tid >= 32) return;
 #else
   const bool warp_tail = false;
 #endif
+  const int tail_nt = warp_tail ? 32 : NT;  // threads that take part in phases D and D2
   auto tail_sync = [&]() {
     if (warp_tail) __syncwarp();
     else __syncthreads();
   };
   if (!s_dense) {
     const int nC = (int)s_nC;
-    for (int base = 0; base < nC; base += NT) {
+    for (int base = 0; base < nC; base += tail_nt) {
       const int i = base + tid;
       const int idx = i < nC ? s_listA[i] : 0;
       const bool surv = i < nC && nms_survives(s_score + idx, SC_W);
@@ -550,7 +565,7 @@ __global__ void __launch_bounds__(NT, PB_FRONT_MIN_CTAS) front_tile_kernel(const
     // ---- phase D2: per bucket keep the bucket_limit largest encoded values, ascending (Fast.h:321-352)
     const int bslots = 1 << (2 * cb_log);
     const int nS = (int)s_nS;
-    for (int i = tid; i < nS; i += NT) {
+    for (int i = tid; i < nS; i += tail_nt) {
       const int s = s_listB[i];
       const uint32_t v = s_cell[s];
       const int b0 = s & ~(bslots - 1);
@@ -581,8 +596,13 @@ __global__ void __launch_bounds__(NT, PB_FRONT_MIN_CTAS) front_tile_kernel(const
   // One warp: lane w owns bitmap word w (a tile keeps a handful of keypoints; 128 threads sweeping all 1024
   // slots cost more than the few set bits).
   if (tid < 32) {
-    const uint32_t w = s_bm[tid];
-    const uint32_t pc = (uint32_t)__popc(w);
+    constexpr int WPL = NCELL / 1024;  // bitmap words per lane (consecutive, so the lane order is the slot order)
+    uint32_t w[WPL], pc = 0;
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) {
+      w[k] = s_bm[tid * WPL + k];
+      pc += (uint32_t)__popc(w[k]);
+    }
     uint32_t incl = pc;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -596,16 +616,18 @@ __global__ void __launch_bounds__(NT, PB_FRONT_MIN_CTAS) front_tile_kernel(const
     const uint32_t excl = incl - pc;
     uint32_t* stage = P.stage + (size_t)frame * P.cap;
     uint32_t pos = base + excl;
-    for (uint32_t bits = w; bits; bits &= bits - 1u) {
-      if (pos < (uint32_t)P.cap) stage[pos] = cells[tid * 32 + (__ffs(bits) - 1)];
-      ++pos;
-    }
-    // a segment is one cell row (64 slots = 2 bitmap words) or one bucket band (64 << cb_log slots)
-    const int seg_words = 2 << cb_log;
-    const int nseg = (NCELL / 32) / seg_words;
-    const uint32_t a = __shfl_sync(0xffffffffu, excl, (tid * seg_words) & 31);
-    const uint32_t bnext = __shfl_sync(0xffffffffu, excl, ((tid + 1) * seg_words) & 31);
-    const uint32_t b = (tid + 1) * seg_words >= NCELL / 32 ? total : bnext;
+#pragma unroll
+    for (int k = 0; k < WPL; ++k)
+      for (uint32_t bits = w[k]; bits; bits &= bits - 1u) {
+        if (pos < (uint32_t)P.cap) stage[pos] = cells[(tid * WPL + k) * 32 + (__ffs(bits) - 1)];
+        ++pos;
+      }
+    // a segment is one cell row (64 slots = 2 bitmap words) or one bucket band (64 << cb_log slots): always whole lanes
+    const int seg_lanes = (2 << cb_log) / WPL;
+    const int nseg = 32 / seg_lanes;
+    const uint32_t a = __shfl_sync(0xffffffffu, excl, (tid * seg_lanes) & 31);
+    const uint32_t bnext = __shfl_sync(0xffffffffu, excl, ((tid + 1) * seg_lanes) & 31);
+    const uint32_t b = (tid + 1) * seg_lanes >= 32 ? total : bnext;
     if (tid < nseg) {
       const size_t pi = (size_t)frame * P.npieces + td.piece0 + tid * L.ntile_cols;
       P.piece_cnt[pi] = b - a;

@@ -252,7 +252,7 @@ int prepare_geometry(pislam_ctx* c, const pislam_pyramid_desc* d, int cap) {
   g.valid = false;
   const int B = d->border;
   const int cb_log = d->log_bucket_size > 0 ? d->log_bucket_size - 1 : 0;
-  const int nseg = 16 >> cb_log;  // segments per tile: cell rows, or bucket bands
+  const int nseg = (TH / 2) >> cb_log;  // segments per tile: cell rows, or bucket bands
   std::vector<TileDesc> tiles;
   int piece = 0;
   long long rows = 0;
