@@ -23,20 +23,44 @@
 namespace pb {
 
 constexpr int TW = 128;             // tile width  (output pixels)
-#ifndef PB_TH
-#define PB_TH 64  // tile height: 64 (measured: 0.310 ms per 256 VGA frames) or 32 (0.347 ms)
-#endif
-constexpr int TH = PB_TH;           // tile height (output pixels)
 constexpr int NT = 128;             // threads per CTA
 constexpr int PIX_W = TW + 32;      // staged pixels: origin (x0-8-dxo, y0-4); a TMA box must start on a
                                     // 16-byte boundary of the row, so dxo = (x0-8) & 15 there, 0 otherwise
-constexpr int PIX_H = TH + 10;
 constexpr int SC_W = TW + 8;        // score tile: origin (x0-4, y0-1)
-constexpr int SC_H = TH + 2;
 constexpr int SC_WW = SC_W / 4;     // score-tile words per row
-constexpr int NWORD = SC_WW * SC_H; // FAST work items (4 pixels each)
-constexpr int CELLS_X = TW / 2, CELLS_Y = TH / 2;
-constexpr int NCELL = CELLS_X * CELLS_Y;  // 2048 (TH 64) / 1024 (TH 32) 2x2 cells per tile
+constexpr int CELLS_X = TW / 2;
+constexpr int A_COLS = SC_WW;       // phase A: 34 word columns
+constexpr int A_ROWS = 5;           // phase A: rows per thread
+
+// Everything that depends on the tile height.  Two heights are compiled: 64 for batches (per-tile set-up, the
+// one-warp tail phases and the halo rows are amortised over twice the pixels: 0.310 vs 0.347 ms per 256 VGA
+// frames) and 32 for calls with few tiles (a single VGA pyramid is 119 tiles of 64 rows for 148 SMs).
+template <int TH_>
+struct TileCfg {
+  static_assert(TH_ == 32 || TH_ == 64, "tile heights 32 and 64 are instantiated");
+  static constexpr int TH = TH_;              // tile height (output pixels)
+  static constexpr int PIX_H = TH + 10;       // staged rows
+  static constexpr int SC_H = TH + 2;         // score-tile rows
+  static constexpr int CELLS_Y = TH / 2;
+  static constexpr int NCELL = CELLS_X * CELLS_Y;  // 2048 / 1024 2x2 cells per tile
+  static constexpr int A_GROUPS = (SC_H + A_ROWS - 1) / A_ROWS;  // 14 / 7 row groups
+  static constexpr int A_TASKS = A_COLS * A_GROUPS;              // 476 / 238 (word column, row group) tasks
+  // rows the last (partly invalid) row group of phase A reads beyond the staged tile: kept inside s_pix by padding
+  static constexpr int PIX_PAD_ROWS = A_GROUPS * A_ROWS + 6 > PIX_H ? A_GROUPS * A_ROWS + 6 - PIX_H : 0;
+  // Work-list capacities.  Natural images need ~130 candidates / ~50 corners per 4096 pixels; the lists are sized
+  // for ~10x that and anything beyond is handled EXACTLY but slowly (inline, then a dense non-max scan), so that
+  // adversarial tiles (noise, checkerboards) stay bit-exact while the common case keeps shared memory small.
+  static constexpr int CAP_A = 2048;   // list A: FAST candidates, later non-zero scores (one per corner <= CAP_B)
+  static constexpr int CAP_B = NCELL;  // list B: FAST corners, later NMS survivors (at most one per cell)
+  // resident CTAs per SM the register budget is set for: 30 KB / 72 registers (TH 64; 6 CTAs measured +7 %),
+  // 18 KB / 48 registers (TH 32; 8: +3 %, 9: +0.7 %, 11-12: +4 % with spills)
+  static constexpr int MIN_CTAS = TH == 64 ? 7 : 10;
+  static_assert(NCELL % 1024 == 0 && NCELL / 32 <= 64, "phase E: one or two bitmap words per lane of one warp");
+  static_assert(CAP_A >= CAP_B && CAP_B >= NCELL, "list A: one entry per corner of list B; list B: one survivor per cell");
+  static_assert(CAP_B * 2 >= ((A_TASKS + 31) & ~31) * 8, "list B hosts the phase-A task list (8 bytes per task)");
+  static_assert(NCELL / 32 + A_COLS + A_GROUPS + 1 <= NT, "set-up roles fit the CTA");
+};
+constexpr int TH_BATCH = 64, TH_SMALL = 32;
 constexpr int MAX_LEVELS = 16;
 
 enum { MODE_TMA = 0, MODE_LDG = 1, MODE_SCOREMAP = 2 };
@@ -217,22 +241,7 @@ __device__ __forceinline__ bool nms_survives(const uint8_t* q, int pitch) {
 // Work lists keep every phase dense: A (SWAR pre-test, all pixels) -> candidates -> B (exact FAST-9)
 // -> corners -> C (Harris code) -> non-zero scores -> D (non-max) -> survivors -> D2 (bucket top-k)
 // -> bitmap over output slots -> E (rank by popcount prefix = the reference's order).
-constexpr int A_COLS = SC_WW;                       // 34 word columns
-constexpr int A_ROWS = 5;                           // rows per phase-A thread
-constexpr int A_GROUPS = (SC_H + A_ROWS - 1) / A_ROWS;  // 14 (TH 64) / 7 (TH 32)
-constexpr int A_TASKS = A_COLS * A_GROUPS;          // 476 / 238 (word column, row group) tasks
-// rows the last (partly invalid) row group of phase A reads beyond the staged tile: kept inside s_pix by padding
-constexpr int PIX_PAD_ROWS = A_GROUPS * A_ROWS + 6 > PIX_H ? A_GROUPS * A_ROWS + 6 - PIX_H : 0;
-static_assert(NCELL % 1024 == 0 && NCELL / 32 <= 64, "phase E: one or two bitmap words per lane of one warp");
 static_assert(A_ROWS == 5, "pretest_rows and the 5-bit row mask are written for 5 rows per task");
-
-// Work-list capacities.  Natural images need ~130 candidates / ~50 corners per tile; the lists are sized for
-// 15x / 20x that and anything beyond is handled EXACTLY but slowly (inline, then a dense non-max scan), so that
-// adversarial tiles (noise, checkerboards) stay bit-exact while the common case keeps 18 KB of shared memory.
-constexpr int CAP_A = 2048;       // list A: FAST candidates, later non-zero scores (at most one per corner <= CAP_B)
-constexpr int CAP_B = NCELL;      // list B: FAST corners, later NMS survivors (at most one per cell)
-static_assert(CAP_A >= CAP_B && CAP_B >= NCELL, "list A holds one entry per corner of list B; list B one survivor per cell");
-static_assert(CAP_B * 2 >= ((A_TASKS + 31) & ~31) * 8, "list B hosts the phase-A task list (8 bytes per task)");
 
 // Slow path of a corner that did not fit into list B: score it in place (rarely executed, kept out of line)
 __device__ __noinline__ void score_corner_inline(const uint8_t* s_pix, uint8_t* s_score, int idx, int dxo,
@@ -258,16 +267,12 @@ __device__ __noinline__ void test_candidate_inline(const uint8_t* s_pix, uint8_t
 #ifndef PB_TAIL_MAX
 #define PB_TAIL_MAX 32  // non-zero scores up to which one warp runs the tail
 #endif
-#ifndef PB_FRONT_MIN_CTAS
-#if PB_TH == 64
-#define PB_FRONT_MIN_CTAS 7  // 30 KB of shared memory per CTA, 72 registers; 6 CTAs/SM (34 KB lists) measured +7 %
-#else
-#define PB_FRONT_MIN_CTAS 10  // 48 registers (32 B of spills); measured: 8 CTAs/SM +3 %, 9 +0.7 %, 11-12 +4 % (spills)
-#endif
-#endif
-template <int MODE>
-__global__ void __launch_bounds__(NT, PB_FRONT_MIN_CTAS) front_tile_kernel(const __grid_constant__ FrontParams P,
-                                                        const __grid_constant__ CUtensorMap tmap) {
+template <int MODE, int TH_>
+__global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(const __grid_constant__ FrontParams P,
+                                                                              const __grid_constant__ CUtensorMap tmap) {
+  using Cfg = TileCfg<TH_>;
+  constexpr int TH = Cfg::TH, PIX_H = Cfg::PIX_H, SC_H = Cfg::SC_H, NCELL = Cfg::NCELL, A_GROUPS = Cfg::A_GROUPS,
+                A_TASKS = Cfg::A_TASKS, PIX_PAD_ROWS = Cfg::PIX_PAD_ROWS, CAP_A = Cfg::CAP_A, CAP_B = Cfg::CAP_B;
   __shared__ __align__(128) uint8_t s_pix[(PIX_H + PIX_PAD_ROWS) * PIX_W];
   __shared__ __align__(16) uint8_t s_score[SC_H * SC_W];
   __shared__ __align__(16) uint16_t s_listA[CAP_A];  // FAST candidates (A->B), then non-zero scores (C->D)
@@ -330,7 +335,6 @@ __global__ void __launch_bounds__(NT, PB_FRONT_MIN_CTAS) front_tile_kernel(const
     const int ilo = min(max(B - y, 0), A_ROWS), ihi = max(min(min(SC_H - r0, ys_end - y), A_ROWS), 0);
     s_vmrow[g] = ilo < ihi ? (((1u << ihi) - 1u) & ~((1u << ilo) - 1u)) * 0x01010101u : 0u;
   }
-  static_assert(NCELL / 32 + A_COLS + A_GROUPS + 1 <= NT, "set-up roles fit the CTA");
 
   if (MODE == MODE_SCOREMAP) {
     __syncthreads();

@@ -130,6 +130,7 @@ struct Geometry {
   pislam_pyramid_desc d;
   int cap = 0;
   bool valid = false;
+  int th = TH_BATCH;  // tile height the tables were built for
   int ntiles = 0, npieces = 0;
   LevelInfo lv[MAX_LEVELS];
   int piece_base[MAX_LEVELS + 1];
@@ -160,8 +161,9 @@ struct pislam_ctx {
   // literal stages
   DevBuf img, out, kp, desc, aux0, aux1;
   // fused path
-  Geometry geo;
-  DevBuf tiles, stage, stage_count, piece_cnt, piece_off, stacks, records, hdr;
+  Geometry geos[2];  // [0] tile height 32 (few tiles), [1] tile height 64 (batches)
+  int gi = 1;        // geometry of the current call
+  DevBuf tiles_th[2], stage, stage_count, piece_cnt, piece_off, stacks, records, hdr;
   // multi-GPU: the all-gather runs on its own stream so that it overlaps the next batch's kernels
   NcclComm comm = nullptr;
   int nranks = 1, rank = 0;
@@ -241,9 +243,23 @@ int validate_desc(const pislam_pyramid_desc* d, int cap, bool fused) {
   return PISLAM_OK;
 }
 
-// Tile + piece tables of a geometry; uploads the tile table when the geometry changed.
-int prepare_geometry(pislam_ctx* c, const pislam_pyramid_desc* d, int cap) {
-  Geometry& g = c->geo;
+// Tile height for a call: 64-row tiles unless they would leave most of the SMs' CTA slots empty
+int pick_tile_height(const pislam_ctx* c, const pislam_pyramid_desc* d, int nframes) {
+  long long tiles64 = 0;
+  for (int l = 0; l < d->nlevels; ++l) {
+    const int iw = d->widths[l] - 2 * d->border, ih = d->heights[l] - 2 * d->border;
+    if (iw > 0 && ih > 0) tiles64 += (long long)((iw + TW - 1) / TW) * ((ih + TH_BATCH - 1) / TH_BATCH);
+  }
+  return tiles64 * nframes < 4LL * c->num_sms ? TH_SMALL : TH_BATCH;
+}
+
+// Tile + piece tables of a geometry (one cached per tile height); uploads the tile table when the geometry changed.
+int prepare_geometry(pislam_ctx* c, const pislam_pyramid_desc* d, int cap, int nframes) {
+  const int TH = pick_tile_height(c, d, nframes);
+  c->gi = TH == TH_BATCH ? 1 : 0;
+  Geometry& g = c->geos[c->gi];
+  DevBuf& tile_buf = c->tiles_th[c->gi];
+  g.th = TH;
   if (g.valid && same_desc(g.d, *d)) {
     g.d = *d;
     g.cap = cap;
@@ -286,10 +302,10 @@ int prepare_geometry(pislam_ctx* c, const pislam_pyramid_desc* d, int cap) {
   g.d = *d;
   g.cap = cap;
   if (g.ntiles > 0) {
-    CK(c->tiles.reserve(tiles.size() * sizeof(TileDesc), false, c->stream));
+    CK(tile_buf.reserve(tiles.size() * sizeof(TileDesc), false, c->stream));
     // the table may still be in use by earlier launches on the stream: stream-ordered copy from a
     // pageable buffer returns once the source has been consumed
-    CK(cudaMemcpyAsync(c->tiles.p, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(tile_buf.p, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
   }
   g.valid = true;
@@ -297,7 +313,7 @@ int prepare_geometry(pislam_ctx* c, const pislam_pyramid_desc* d, int cap) {
 }
 
 int make_tensor_map(pislam_ctx* c, CUtensorMap* m, const uint8_t* base, int vstep, long long rows, int nframes,
-                    size_t frame_stride, int box_w = PIX_W, int box_h = PIX_H) {
+                    size_t frame_stride, int box_w, int box_h) {
   const cuuint64_t dims[3] = {(cuuint64_t)vstep, (cuuint64_t)rows, (cuuint64_t)nframes};
   const cuuint64_t strides[2] = {(cuuint64_t)vstep, (cuuint64_t)(nframes > 1 ? frame_stride : (size_t)rows * vstep)};
   const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
@@ -309,7 +325,7 @@ int make_tensor_map(pislam_ctx* c, CUtensorMap* m, const uint8_t* base, int vste
 }
 
 void fill_front_params(const pislam_ctx* c, FrontParams& P, const uint8_t* src, size_t frame_stride) {
-  const Geometry& g = c->geo;
+  const Geometry& g = c->geos[c->gi];
   memset(&P, 0, sizeof(P));
   P.src = src;
   P.frame_stride = frame_stride;
@@ -323,7 +339,7 @@ void fill_front_params(const pislam_ctx* c, FrontParams& P, const uint8_t* src, 
   P.bucket_limit = g.d.bucket_limit;
   P.cap = g.cap;
   P.npieces = g.npieces;
-  P.tiles = c->tiles.as<TileDesc>();
+  P.tiles = c->tiles_th[c->gi].as<TileDesc>();
   P.stage = c->stage.as<uint32_t>();
   P.stage_count = c->stage_count.as<uint32_t>();
   P.piece_cnt = c->piece_cnt.as<uint32_t>();
@@ -331,7 +347,7 @@ void fill_front_params(const pislam_ctx* c, FrontParams& P, const uint8_t* src, 
 }
 
 int reserve_front_scratch(pislam_ctx* c, int nframes) {
-  const Geometry& g = c->geo;
+  const Geometry& g = c->geos[c->gi];
   CK(c->stage.reserve((size_t)nframes * g.cap * 4, false, c->stream));
   CK(c->stage_count.reserve((size_t)nframes * 4, true, c->stream));
   CK(c->piece_cnt.reserve((size_t)nframes * std::max(1, g.npieces) * 4, false, c->stream));
@@ -340,7 +356,7 @@ int reserve_front_scratch(pislam_ctx* c, int nframes) {
 }
 
 int launch_order(pislam_ctx* c, int nframes, int words, uint8_t* d_records) {
-  const Geometry& g = c->geo;
+  const Geometry& g = c->geos[c->gi];
   OrderParams O;
   memset(&O, 0, sizeof(O));
   O.nlevels = g.d.nlevels;
@@ -364,8 +380,8 @@ int enqueue_extract(pislam_ctx* c, const uint8_t* d_stacks, size_t frame_stride,
                     const pislam_pyramid_desc* d, int cap, uint8_t* d_records) {
   if (!d_stacks || !d_records || nframes < 1 || nframes > 65535) return PISLAM_ERR_INVALID_ARG;
   CKS(validate_desc(d, cap, true));
-  CKS(prepare_geometry(c, d, cap));
-  const Geometry& g = c->geo;
+  CKS(prepare_geometry(c, d, cap, nframes));
+  const Geometry& g = c->geos[c->gi];
   if (nframes > 1 && frame_stride < (size_t)g.rows * d->vstep) return PISLAM_ERR_INVALID_ARG;
   if (nframes == 1) frame_stride = (size_t)g.rows * d->vstep;
   CKS(reserve_front_scratch(c, nframes));
@@ -380,10 +396,15 @@ int enqueue_extract(pislam_ctx* c, const uint8_t* d_stacks, size_t frame_stride,
     span_begin(c, 0);
     // occupancy experiments: extra (unused) dynamic shared memory per CTA
     static const int pad = getenv("PISLAM_B200_DEBUG_SMEM_PAD") ? atoi(getenv("PISLAM_B200_DEBUG_SMEM_PAD")) : 0;
-    if (tma_ok && make_tensor_map(c, &tmap, d_stacks, d->vstep, g.rows, nframes, frame_stride) == PISLAM_OK)
-      front_tile_kernel<MODE_TMA><<<grid, NT, pad, c->stream>>>(P, tmap);
-    else
-      front_tile_kernel<MODE_LDG><<<grid, NT, 0, c->stream>>>(P, tmap);
+    const int box_h = g.th == TH_BATCH ? TileCfg<TH_BATCH>::PIX_H : TileCfg<TH_SMALL>::PIX_H;
+    const bool tma = tma_ok && make_tensor_map(c, &tmap, d_stacks, d->vstep, g.rows, nframes, frame_stride, PIX_W, box_h) == PISLAM_OK;
+    if (g.th == TH_BATCH) {
+      if (tma) front_tile_kernel<MODE_TMA, TH_BATCH><<<grid, NT, pad, c->stream>>>(P, tmap);
+      else front_tile_kernel<MODE_LDG, TH_BATCH><<<grid, NT, 0, c->stream>>>(P, tmap);
+    } else {
+      if (tma) front_tile_kernel<MODE_TMA, TH_SMALL><<<grid, NT, pad, c->stream>>>(P, tmap);
+      else front_tile_kernel<MODE_LDG, TH_SMALL><<<grid, NT, 0, c->stream>>>(P, tmap);
+    }
     span_end(c);
     CKS(check_launch(c));
   }
@@ -570,7 +591,7 @@ int pislam_b200_destroy(pislam_ctx* c) {
   if (c->copy_out) cudaStreamSynchronize(c->copy_out);
   if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-  DevBuf* bufs[] = {&c->img, &c->out, &c->kp, &c->desc, &c->aux0, &c->aux1, &c->tiles, &c->stage, &c->stage_count,
+  DevBuf* bufs[] = {&c->img, &c->out, &c->kp, &c->desc, &c->aux0, &c->aux1, &c->tiles_th[0], &c->tiles_th[1], &c->stage, &c->stage_count,
                     &c->piece_cnt, &c->piece_off, &c->stacks, &c->records, &c->hdr};
   for (DevBuf* b : bufs) b->release();
   if (c->d_brief) cudaFree(c->d_brief);
@@ -720,7 +741,7 @@ int pislam_b200_fast_extract(pislam_ctx* c, const uint8_t* out, int vstep, int b
   const int maxkp = ((iw + 1) / 2) * ((ih + 1) / 2);
   const int dcap = std::max(1, std::min(maxkp, std::max(cap, 1)));
   CKS(validate_desc(&d, dcap, false));
-  CKS(prepare_geometry(c, &d, dcap));
+  CKS(prepare_geometry(c, &d, dcap, 1));
   const size_t bytes = (size_t)height * vstep;
   CK(c->out.reserve(bytes, false, c->stream));
   CK(cudaMemcpyAsync(c->out.p, out, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -731,7 +752,10 @@ int pislam_b200_fast_extract(pislam_ctx* c, const uint8_t* out, int vstep, int b
   fill_front_params(c, P, c->out.as<uint8_t>(), bytes);
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
-  front_tile_kernel<MODE_SCOREMAP><<<dim3(c->geo.ntiles, 1), NT, 0, c->stream>>>(P, tmap);
+  if (c->geos[c->gi].th == TH_BATCH)
+    front_tile_kernel<MODE_SCOREMAP, TH_BATCH><<<dim3(c->geos[c->gi].ntiles, 1), NT, 0, c->stream>>>(P, tmap);
+  else
+    front_tile_kernel<MODE_SCOREMAP, TH_SMALL><<<dim3(c->geos[c->gi].ntiles, 1), NT, 0, c->stream>>>(P, tmap);
   CKS(check_launch(c));
   CKS(launch_order(c, 1, 0, c->records.as<uint8_t>()));
   uint32_t header[2];
@@ -944,9 +968,9 @@ int pislam_b200_extract_batch(pislam_ctx* c, const uint8_t* stacks, size_t frame
     const size_t total = (size_t)(nframes - 1) * frame_stride + frame_bytes;
     CK(c->stacks.reserve(total, false, c->stream));
     uint8_t* d_stacks = c->stacks.as<uint8_t>();
-    CKS(prepare_geometry(c, d, cap));
     const int nchunks = std::max(1, std::min(c->pipeline_chunks, nframes));
     const int per = (nframes + nchunks - 1) / nchunks;
+    CKS(prepare_geometry(c, d, cap, per));
     CKS(reserve_front_scratch(c, per));
     // earlier work on the ctx stream may still read the staging buffer
     CK(cudaEventRecord(c->ev_k[0], c->stream));
