@@ -4,7 +4,8 @@
     python tools/ncu_by_line.py <report.ncu-rep> <kernel-substring> [top]
 
 ncu's CSV source page is per SASS instruction; the line table comes from `nvdisasm -g` on the cubin
-embedded in pislam_b200/lib/libpislam_b200.so (must be the build that was profiled).
+embedded in pislam_b200/lib/libpislam_b200.so (must be the build that was profiled).  The substring must select ONE
+kernel instantiation of the cubin, e.g. front_tile_kernelILi0ELi64 (MODE_TMA, 128x64 tiles) or orb_tma_kernel.
 """
 import csv
 import io
