@@ -21,9 +21,17 @@ with api.Context(0) as ctx:
                 ok &= good
                 print(name, "buckets", (lb, bl), "tma", tma, "n", len(kp), "match", good)
     ctx.set_tma(1)
-    stacks = np.stack([synthetic_stack(lay, 20 + i) for i in range(6)])
-    res = ctx.extract_batch(stacks, api.make_desc(lay, log_bucket=4, bucket_limit=3), cap=2048)
-    print("batch", [len(r[0]) for r in res])
+    # 48 frames: enough tiles for the host to pick the 128x64 instantiation (single frames above use 128x32)
+    src = [synthetic_stack(lay, 20 + i) for i in range(5)] + [noise_stack(lay, 9)]
+    stacks = np.stack([src[i % 6] for i in range(48)])
+    for lb, bl in ((4, 3), (0, 5)):
+        res = ctx.extract_batch(stacks, api.make_desc(lay, log_bucket=lb, bucket_limit=bl), cap=1 << 15)
+        for i in range(6):
+            okp, olv, odesc = o.extract_pyramid(src[i], lay.widths, lay.heights, lay.row_offsets, log_bucket=lb,
+                                                bucket_limit=bl, cap=1 << 15)
+            good = all(np.array_equal(res[j][0], okp) and np.array_equal(res[j][2], odesc) for j in range(i, 48, 6))
+            ok &= good
+            print("batch frame", i, "buckets", (lb, bl), "n", len(okp), "match", good)
     img = np.ascontiguousarray(stack[:240])
     out = np.zeros_like(img)
     ctx.fastDetect(320, 240, img, out, 20)
