@@ -597,8 +597,8 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
   }
 
   // ---- phase E: rank by slot = popcount prefix over the slot bitmap; one staging segment per tile ----
-  // One warp: lane w owns bitmap word w (a tile keeps a handful of keypoints; 128 threads sweeping all 1024
-  // slots cost more than the few set bits).
+  // One warp: lane w owns WPL consecutive bitmap words (a tile keeps a handful of keypoints; 128 threads sweeping
+  // all slots cost more than the few set bits).
   if (tid < 32) {
     constexpr int WPL = NCELL / 1024;  // bitmap words per lane (consecutive, so the lane order is the slot order)
     uint32_t w[WPL], pc = 0;
