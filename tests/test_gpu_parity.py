@@ -51,6 +51,43 @@ def test_literal_stages_small_golden(ctx, golden):
                     golden["small%d_kp_b4_3" % i], "fastExtract<4,3> case %d" % i)
 
 
+def test_literal_stages_random_ragged(ctx, oracle):
+    """Seeded sweep over ragged level sizes, borders 16/9/4, thresholds (incl. 0, >= 128, > 255, negative), bucket
+    settings and two image statistics -- the sweep tests/test_oracle.py runs oracle-vs-reference, here CUDA-vs-oracle."""
+    rng = np.random.Generator(np.random.PCG64(2025))
+    for vstep in (128, 96, 200):
+        for border in (16, 9, 4):
+            for _ in range(5):
+                w = int(rng.integers(2 * border + 3, vstep + 1))
+                h = int(rng.integers(2 * border + 3, 90))
+                rows = h + 8
+                if rng.integers(0, 2):
+                    img = rng.integers(0, 256, size=(rows, vstep), dtype=np.uint8)
+                else:
+                    coarse = rng.integers(0, 256, size=(rows // 6 + 2, vstep // 6 + 2), dtype=np.uint8)
+                    img = np.kron(coarse, np.ones((6, 6), np.uint8))[:rows, :vstep].copy()
+                    img = np.clip(img.astype(np.int32) + rng.integers(-3, 4, size=img.shape), 0, 255).astype(np.uint8)
+                ft = int(rng.choice([0, 1, 7, 20, 35, 90, 127, 128, 200, 255, 300, -5]))
+                ht = int(rng.choice([-(1 << 20), 0, 1 << 8, 1 << 13, 1 << 15, 1 << 22]))
+                lb, bl = int(rng.integers(0, 6)), int(rng.integers(1, 7))
+                tag = "vstep %d border %d w %d h %d ft %d ht %d buckets %s" % (vstep, border, w, h, ft, ht, (lb, bl))
+                want = np.zeros_like(img)
+                oracle.fast_detect(img, want, border, w, h, ft)
+                out = np.zeros_like(img)
+                ctx.fastDetect(w, h, img, out, ft, border=border)
+                assert_same(out, want, "fastDetect " + tag)
+                oracle.fast_score_harris(img, want, border, w, h, ht)
+                ctx.fastScoreHarris(w, h, img, ht, out, border=border)
+                assert_same(out, want, "fastScoreHarris " + tag)
+                okp = oracle.fast_extract(want, border, w, h, lb, bl, cap=1 << 16)
+                kp = ctx.fastExtract(w, h, out, border=border, logBucketSize=lb, bucketLimit=bl)
+                assert_same(kp, okp, "fastExtract " + tag)
+                if border == 16 and len(okp):
+                    for words in (8, 3):
+                        assert_same(ctx.orbCompute(img, okp, words=words), oracle.orb_compute(img, okp, words),
+                                    "orbCompute words %d %s" % (words, tag))
+
+
 def test_fast_detect_preserves_untouched_bytes(ctx, golden, oracle):
     """The reference only writes rows [border,h-border) x the 16-px blocks; everything else in `out` stays."""
     vstep, w, h, border, ft, ht = golden["small_params"].tolist()[1]

@@ -150,3 +150,43 @@ def test_live_reference_harris_thresholds(reference, oracle):
         for _ in range(200):
             x, y = int(rng.integers(3, 120)), int(rng.integers(3, 59))
             assert oracle.harris_score_sobel(img, x, y, thr) == reference.harris_score_sobel(img, x, y, thr)
+
+
+def test_live_reference_random_ragged_levels(reference, oracle):
+    """Seeded sweep over ragged level sizes (every residue of w-2B modulo 16 and 2), the borders / bucket settings
+    the reference driver instantiates, random thresholds and two image statistics: the C restatement must equal
+    the reference's own headers for fastDetect, fastScoreHarris, fastExtract (and orbCompute at border 16)."""
+    rng = np.random.Generator(np.random.PCG64(2024))
+    buckets = [(0, 5), (4, 3), (4, 5), (3, 2), (5, 4)]
+    ncases = 0
+    for vstep in (128, 96):
+        for border in (16, 9, 4):
+            for _ in range(10):
+                w = int(rng.integers(2 * border + 3, vstep + 1))
+                h = int(rng.integers(2 * border + 3, 90))
+                rows = h + 8
+                if rng.integers(0, 2):
+                    img = rng.integers(0, 256, size=(rows, vstep), dtype=np.uint8)
+                else:  # blocky image with mild noise: real corners, ties in the score map
+                    coarse = rng.integers(0, 256, size=(rows // 6 + 2, vstep // 6 + 2), dtype=np.uint8)
+                    img = np.kron(coarse, np.ones((6, 6), np.uint8))[:rows, :vstep].copy()
+                    img = np.clip(img.astype(np.int32) + rng.integers(-3, 4, size=img.shape), 0, 255).astype(np.uint8)
+                ft = int(rng.choice([0, 1, 7, 20, 35, 90, 127, 128, 200, 255, 300, -5]))
+                ht = int(rng.choice([-(1 << 20), 0, 1 << 8, 1 << 13, 1 << 15, 1 << 22]))
+                lb, bl = buckets[int(rng.integers(0, len(buckets)))]
+                outs, kps = [], []
+                for lib in (oracle, reference):
+                    out = np.zeros_like(img)
+                    lib.fast_detect(img, out, border, w, h, ft)
+                    lib.fast_score_harris(img, out, border, w, h, ht)
+                    outs.append(out)
+                    kps.append(lib.fast_extract(out, border, w, h, lb, bl, cap=1 << 16))
+                tag = "vstep %d border %d w %d h %d ft %d ht %d buckets %s" % (vstep, border, w, h, ft, ht, (lb, bl))
+                assert np.array_equal(outs[0], outs[1]), tag
+                assert np.array_equal(kps[0], kps[1]), tag
+                if border == 16 and len(kps[0]):
+                    for words in ((8, 5) if vstep == 128 else (8,)):  # the driver's orbCompute<vstep,words> menu
+                        assert np.array_equal(oracle.orb_compute(img, kps[0], words),
+                                              reference.orb_compute(img, kps[0], words)), tag
+                ncases += 1
+    assert ncases == 60
