@@ -50,15 +50,19 @@ void* pislam_b200_stream(pislam_ctx* ctx);
 int pislam_b200_synchronize(pislam_ctx* ctx);
 /* Number of kernel launches issued by this ctx since creation (bench.py's gpu_launches). */
 long pislam_b200_launch_count(pislam_ctx* ctx);
+/* Number of tile-table uploads so far: the fused calls cache the tile / piece tables of the last few pyramid
+ * geometries per ctx (LRU), so a caller alternating a handful of geometries uploads each of them once. */
+long pislam_b200_geometry_uploads(pislam_ctx* ctx);
 /* Tile staging of the fused kernel: 1 = TMA box loads (default), 0 = plain loads.  The TMA path is also
  * skipped automatically when vstep / frame_stride / the base address are not multiples of 16 bytes. */
 int pislam_b200_set_tma(pislam_ctx* ctx, int enable);
 /* Per-kernel timing of the fused path (bench.py's roofline): while enabled, CUDA events are recorded on
- * the ctx stream around every launch of [0] front_tile_kernel, [1] order_kernel, [2] orb_kernel.
+ * the ctx stream around every launch of [0] front_tile_kernel, [1] order_kernel, [2] orb_kernel,
+ * [3] pyramid_build_kernel.
  * pislam_b200_kernel_times synchronises, returns the summed durations (ms) and launch counts since the
  * last call, and clears them. */
 int pislam_b200_set_profiling(pislam_ctx* ctx, int enable);
-int pislam_b200_kernel_times(pislam_ctx* ctx, double ms[3], long count[3]);
+int pislam_b200_kernel_times(pislam_ctx* ctx, double ms[4], long count[4]);
 
 /* ---- literal stages (host buffers) ---------------------------------------------------------- */
 /* pislam::fastDetect<vstep,border>(width,height,img,out,threshold)        reference Fast.h:54-158 */
@@ -150,20 +154,48 @@ int pislam_b200_extract_batch_async(pislam_ctx* ctx, const uint8_t* d_stacks, si
 int pislam_b200_extract_pyramid(pislam_ctx* ctx, const uint8_t* stack, const pislam_pyramid_desc* desc,
                                 uint32_t* kp, uint8_t* kp_level, uint32_t* descriptors, int cap, int* n);
 
+/* ---- pyramid builder in front of the path --------------------------
+ * The reference consumes a pre-built stacked pyramid and leaves its construction to the caller
+ * ("externally computing the image pyramid", reference README.md:28-31) -- on a GPU, it suggests.  These two
+ * entry points do that on the device, so that only the BASE frame crosses PCIe (1/3 of the stack's level
+ * pixels for 8 levels at x1/1.2).  NOT a replacement of reference code: the reference ships no x1/1.2
+ * resize, so the definition is this library's own and its parity is unpinned by the reference
+ * (oracle/pislam_oracle.h: po_resize_bilinear / po_build_pyramid; the CUDA path is bit-exact to those).
+ *   level l = pixel-centre-aligned bilinear resize of the base frame (widths[0] x heights[0]) to
+ *   widths[l] x heights[l]: 8.8 fixed-point positions, 8-bit weights, one rounding; level 0 is the base
+ *   frame itself.  blur != 0 first applies pislam::gaussian5x5 (reference Gaussian.h:48-72) to the base
+ *   frame -- the reference expects pre-blurred input (README.md:28-31).
+ * frames: nframes base frames, row pitch frame_pitch, frame f at frames + f*frame_stride; host or device. */
+/* base frames -> stacked pyramids in the layout `desc` describes (rows of the stack that belong to no level are
+ * left as they are; columns right of each level are zero-filled).  stacks: host or device. */
+int pislam_b200_build_pyramid(pislam_ctx* ctx, const uint8_t* frames, int frame_pitch, size_t frame_stride,
+                              int nframes, int blur, const pislam_pyramid_desc* desc, uint8_t* stacks,
+                              size_t stack_stride);
+/* base frames -> records: pislam_b200_build_pyramid into device memory followed by the fused path of
+ * pislam_b200_extract_batch, chunk by chunk (host frames: H2D of chunk i+1 under the kernels of chunk i under
+ * the D2H of the records of chunk i-1).  Same records, status and capacity behaviour as extract_batch on the
+ * stacks build_pyramid would produce. */
+int pislam_b200_extract_frames(pislam_ctx* ctx, const uint8_t* frames, int frame_pitch, size_t frame_stride,
+                               int nframes, int blur, const pislam_pyramid_desc* desc, int cap, void* records);
+
 /* ---- multi-GPU: frames shard one-per-rank, results meet in ONE all-gather --------------------- */
 /* 128-byte ncclUniqueId; create on rank 0, distribute with any host-side channel. */
 int pislam_b200_comm_unique_id(void* id128);
 int pislam_b200_comm_init(pislam_ctx* ctx, int nranks, int rank, const void* id128);
 int pislam_b200_comm_destroy(pislam_ctx* ctx);
-/* extract_batch on this rank's `nframes_local` frames, then a single ncclAllGather of the
- * fixed-capacity records: d_all_records (device) receives nranks * nframes_local * record_bytes,
- * rank-major; the kernels write this rank's records straight into its slot (in-place gather).
+/* extract_batch on this rank's `nframes_local` frames (0 <= nframes_local <= slots_per_rank), then a single
+ * ncclAllGather of the fixed-capacity records: d_all_records (device) receives
+ * nranks * slots_per_rank * record_bytes, rank-major; the kernels write this rank's records straight into
+ * its slot (in-place gather).  `slots_per_rank` must be the same on every rank (ceil(total frames / nranks)
+ * for a contiguous split: trailing ranks may own fewer frames, or none); the unused slots of a rank arrive
+ * with an all-zero header (n = 0).  Arguments are validated before anything is enqueued, and once the kernels
+ * are enqueued the collective is always issued, so a failing rank never leaves its peers waiting.
  * The gather is issued on a second stream behind the kernels, so with two alternating gather
  * buffers it overlaps the next batch's kernels; a buffer is never rewritten before its previous
  * gather has finished.  Enqueue only: pislam_b200_synchronize waits for kernels and gathers. */
 int pislam_b200_extract_allgather(pislam_ctx* ctx, const uint8_t* d_stacks, size_t frame_stride,
-                                  int nframes_local, const pislam_pyramid_desc* desc, int cap,
-                                  void* d_all_records);
+                                  int nframes_local, int slots_per_rank, const pislam_pyramid_desc* desc,
+                                  int cap, void* d_all_records);
 
 /* Makes the ctx stream wait (on the device) for the gathers issued so far by pislam_b200_extract_allgather,
  * so that later work -- or an event recorded -- on the ctx stream is ordered after them. */

@@ -460,6 +460,58 @@ void po_bilinear13_16(const uint8_t* img, uint8_t* out, int vstep, int width, in
   free(src);
 }
 
+/* ------------------------------------------------------------------ pyramid builder
+ * Not reference code: the reference leaves the x1/1.2 pyramid to its caller (README.md:28-31).  Restates
+ * pislam_b200/pyramid.py:_resize_bilinear (the definition this repo's synthetic pyramids are built with). */
+static void resize_taps(int n_out, int n_in, int i, int* i0, int* i1, int* f) {
+  long pos = ((long)(2 * i + 1) * n_in * 128) / n_out - 128; /* 8.8 fixed point, floor division of a positive value */
+  const long hi = (long)(n_in - 1) * 256;
+  if (pos < 0) pos = 0;
+  if (pos > hi) pos = hi;
+  *i0 = (int)(pos >> 8);
+  *f = (int)(pos & 255);
+  *i1 = *i0 + 1 < n_in ? *i0 + 1 : n_in - 1;
+}
+
+void po_resize_bilinear(const uint8_t* src, int src_pitch, int sw, int sh, uint8_t* dst, int dst_pitch, int dw,
+                        int dh) {
+  for (int y = 0; y < dh; ++y) {
+    int y0, y1, fy;
+    resize_taps(dh, sh, y, &y0, &y1, &fy);
+    const uint8_t* r0 = src + (long)y0 * src_pitch;
+    const uint8_t* r1 = src + (long)y1 * src_pitch;
+    for (int x = 0; x < dw; ++x) {
+      int x0, x1, fx;
+      resize_taps(dw, sw, x, &x0, &x1, &fx);
+      const int top = r0[x0] * (256 - fx) + r0[x1] * fx;
+      const int bot = r1[x0] * (256 - fx) + r1[x1] * fx;
+      dst[(long)y * dst_pitch + x] = (uint8_t)((top * (256 - fy) + bot * fy + (1 << 15)) >> 16);
+    }
+  }
+}
+
+void po_build_pyramid(const uint8_t* base, int base_pitch, int blur, int vstep, int nlevels, const int* widths,
+                      const int* heights, const int* row_offsets, uint8_t* stack) {
+  const int W = widths[0], H = heights[0];
+  uint8_t* tmp = NULL;
+  if (blur) {
+    tmp = (uint8_t*)malloc((size_t)W * H);
+    /* po_gaussian5x5 takes one pitch for input and output: blur through a pitch-W copy */
+    uint8_t* in = (uint8_t*)malloc((size_t)W * H);
+    for (int y = 0; y < H; ++y) memcpy(in + (long)y * W, base + (long)y * base_pitch, W);
+    po_gaussian5x5(in, tmp, W, W, H);
+    free(in);
+    base = tmp;
+    base_pitch = W;
+  }
+  for (int l = 0; l < nlevels; ++l) {
+    uint8_t* lvl = stack + (long)row_offsets[l] * vstep;
+    po_resize_bilinear(base, base_pitch, W, H, lvl, vstep, widths[l], heights[l]);
+    for (int y = 0; y < heights[l]; ++y) memset(lvl + (long)y * vstep + widths[l], 0, vstep - widths[l]);
+  }
+  free(tmp);
+}
+
 /* ------------------------------------------------------------------ all-host-cores baseline */
 typedef struct {
   const uint8_t* stacks;

@@ -16,8 +16,10 @@
 // combination outside the menu returns -1.
 //
 // Built by oracle/Makefile into oracle/_ref/libpislam_ref.so (git-ignored).
+#include <atomic>
 #include <cstdint>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "arm_neon.h"   // oracle/neon_shim
@@ -153,6 +155,81 @@ int ref_bilinear13_16(uint8_t* img, uint8_t* out, int vstep, int width, int heig
   REF_VSTEPS(CASE)
 #undef CASE
   return -1;
+}
+
+// The reference's caller loop (demo/demo.cpp:77-101, README.md:56-83) over a batch of stacked pyramids, one whole
+// pyramid per task on `nthreads` std::threads -- the reference itself is single-threaded (nthreads = 1 is its
+// own shape; more threads = "all host cores" of bench.py's CPU arm).  No Python between the stages.
+// `out` is zeroed per frame (Fast.h:42-44 requires it); orbCompute runs per level on level-local keypoints, which
+// yields the same descriptors as the demo's single call on stack coordinates and stays valid for stacks taller than
+// the 12-bit y range (1080p, 4K).  counts[f] = keypoints of frame f; kp / desc (optional) are [nframes][cap] and
+// [nframes][cap*8].  Returns 0, -1 for a (vstep, bucket) combination outside the instantiated menu, -2 if cap is
+// too small.
+}  // extern "C"
+
+template <int V, int L, int K>
+static int ref_frame(const uint8_t* stack, uint8_t* out, long rows, int nlevels, const int* widths,
+                     const int* heights, const int* row_offsets, int fast_t, int32_t harris_t,
+                     std::vector<uint32_t>& points, std::vector<uint32_t>& desc) {
+  std::memset(out, 0, (size_t)rows * V);
+  points.clear();
+  desc.clear();
+  for (int l = 0; l < nlevels; ++l) {
+    uint8_t(*img)[V] = (uint8_t(*)[V])(stack + (size_t)row_offsets[l] * V);
+    uint8_t(*o)[V] = (uint8_t(*)[V])(out + (size_t)row_offsets[l] * V);
+    std::vector<uint32_t> lvl;
+    pislam::fastDetect<V, 16>(widths[l], heights[l], img, o, fast_t);
+    pislam::fastScoreHarris<V, 16>(widths[l], heights[l], img, harris_t, o);
+    pislam::fastExtract<V, 16, L, K>(widths[l], heights[l], o, lvl);
+    pislam::orbCompute<V, 8>(img, lvl, desc);
+    points.insert(points.end(), lvl.begin(), lvl.end());
+  }
+  return (int)points.size();
+}
+
+extern "C" {
+
+int ref_extract_batch(const uint8_t* stacks, long frame_stride, int nframes, int vstep, int nlevels,
+                      const int* widths, const int* heights, const int* row_offsets, int fast_t,
+                      int32_t harris_t, int logBucketSize, int bucketLimit, int cap, int nthreads,
+                      int* counts, uint32_t* kp, uint32_t* desc) {
+  typedef int (*FrameFn)(const uint8_t*, uint8_t*, long, int, const int*, const int*, const int*, int, int32_t,
+                         std::vector<uint32_t>&, std::vector<uint32_t>&);
+  FrameFn fn = nullptr;
+#define CASE(V, B, L, K) \
+  if (vstep == V && logBucketSize == L && bucketLimit == K) fn = ref_frame<V, L, K>;
+#define PER_V(V) REF_BUCKETS(CASE, V, 16)
+  PER_V(640) PER_V(1920) PER_V(3840)
+#undef PER_V
+#undef CASE
+  if (!fn) return -1;
+  long rows = 0;
+  for (int l = 0; l < nlevels; ++l)
+    if (row_offsets[l] + heights[l] > rows) rows = row_offsets[l] + heights[l];
+  std::atomic<int> next(0), status(0);
+  auto work = [&]() {
+    std::vector<uint8_t> out((size_t)rows * vstep + 64);
+    std::vector<uint32_t> points, d;
+    for (;;) {
+      const int f = next.fetch_add(1);
+      if (f >= nframes) break;
+      const int n = fn(stacks + (size_t)f * frame_stride, out.data(), rows, nlevels, widths, heights, row_offsets,
+                       fast_t, harris_t, points, d);
+      counts[f] = n;
+      if (n > cap) {
+        status = -2;
+        continue;
+      }
+      if (kp) std::memcpy(kp + (size_t)f * cap, points.data(), (size_t)n * 4);
+      if (desc) std::memcpy(desc + (size_t)f * cap * 8, d.data(), (size_t)n * 32);
+    }
+  };
+  if (nthreads < 1) nthreads = 1;
+  std::vector<std::thread> th;
+  for (int i = 1; i < nthreads; ++i) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+  return status;
 }
 
 uint32_t ref_encode_fast(uint32_t score, uint32_t x, uint32_t y) { return pislam::encodeFast(score, x, y); }

@@ -51,9 +51,14 @@ _SIGNATURES = {
     "pislam_b200_stream": (C.c_void_p, [C.c_void_p]),
     "pislam_b200_synchronize": (C.c_int, [C.c_void_p]),
     "pislam_b200_launch_count": (C.c_long, [C.c_void_p]),
+    "pislam_b200_geometry_uploads": (C.c_long, [C.c_void_p]),
     "pislam_b200_set_tma": (C.c_int, [C.c_void_p, C.c_int]),
     "pislam_b200_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "pislam_b200_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_long)]),
+    "pislam_b200_build_pyramid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_int,
+                                            C.POINTER(PyramidDesc), C.c_void_p, C.c_size_t]),
+    "pislam_b200_extract_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_int,
+                                             C.POINTER(PyramidDesc), C.c_int, C.c_void_p]),
     "pislam_b200_fast_detect": (C.c_int, [C.c_void_p, _u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "pislam_b200_fast_score_harris": (C.c_int, [C.c_void_p, _u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int,
                                                 C.c_int32]),
@@ -83,7 +88,7 @@ _SIGNATURES = {
     "pislam_b200_comm_unique_id": (C.c_int, [C.c_void_p]),
     "pislam_b200_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "pislam_b200_comm_destroy": (C.c_int, [C.c_void_p]),
-    "pislam_b200_extract_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+    "pislam_b200_extract_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                                                 C.POINTER(PyramidDesc), C.c_int, C.c_void_p]),
     "pislam_b200_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "pislam_b200_join": (C.c_int, [C.c_void_p]),
@@ -209,6 +214,10 @@ class Context:
     def launch_count(self):
         return self.lib.pislam_b200_launch_count(self._h)
 
+    @property
+    def geometry_uploads(self):
+        return self.lib.pislam_b200_geometry_uploads(self._h)
+
     def synchronize(self):
         self._ok(self.lib.pislam_b200_synchronize(self._h))
 
@@ -216,9 +225,10 @@ class Context:
         self._ok(self.lib.pislam_b200_set_profiling(self._h, int(bool(enable))))
 
     def kernel_times(self):
-        """(ms[3], count[3]) for front_tile_kernel, order_kernel, orb_kernel since the last call."""
-        ms = (C.c_double * 3)()
-        cnt = (C.c_long * 3)()
+        """(ms[4], count[4]) for front_tile_kernel, order_kernel, orb_kernel, pyramid_build_kernel since the
+        last call."""
+        ms = (C.c_double * 4)()
+        cnt = (C.c_long * 4)()
         self._ok(self.lib.pislam_b200_kernel_times(self._h, ms, cnt))
         return list(ms), list(cnt)
 
@@ -351,6 +361,10 @@ class Context:
     def extract_pyramid(self, stack, desc, cap=4096):
         """One stacked pyramid (host array) -> (kp, level, descriptors)."""
         _check_img(stack, "stack")
+        rows = max(desc.row_offsets[i] + desc.heights[i] for i in range(desc.nlevels))
+        if stack.shape[1] != desc.vstep or stack.shape[0] < rows:
+            raise ValueError("stack shape %s does not hold the described pyramid (%d rows x %d)" % (
+                stack.shape, rows, desc.vstep))
         kp = np.zeros(cap, np.uint32)
         lv = np.zeros(cap, np.uint8)
         d = np.zeros((cap, max(1, desc.words)), np.uint32)
@@ -366,6 +380,10 @@ class Context:
     def extract_batch(self, stacks, desc, cap=4096):
         """stacks: host uint8 [nframes][rows][vstep] -> list of (kp, level, desc, level_start, n_total)."""
         assert stacks.dtype == np.uint8 and stacks.ndim == 3 and stacks.flags.c_contiguous
+        rows = max(desc.row_offsets[i] + desc.heights[i] for i in range(desc.nlevels))
+        if stacks.shape[2] != desc.vstep or stacks.shape[1] < rows:
+            raise ValueError("stacks shape %s does not hold the described pyramid (%d rows x %d)" % (
+                stacks.shape, rows, desc.vstep))
         nf = stacks.shape[0]
         lay = record_layout(cap, desc.words)
         rec = np.zeros(nf * lay["bytes"], np.uint8)
@@ -374,6 +392,38 @@ class Context:
         if st != PISLAM_ERR_CAPACITY:
             self._ok(st)
         return parse_records(rec, nf, cap, desc.words)
+
+    # ---- pyramid builder in front of the path (include/pislam_b200.h) -----------------
+    def build_pyramid(self, frames, desc, blur=False, fill=0):
+        """frames: host uint8 [nframes][H][W] base frames -> stacks uint8 [nframes][rows][vstep]."""
+        frames = np.ascontiguousarray(frames)
+        assert frames.dtype == np.uint8 and frames.ndim == 3
+        nf, H, W = frames.shape
+        assert (W, H) == (desc.widths[0], desc.heights[0]), "base frames must have the size of level 0"
+        rows = max(desc.row_offsets[i] + desc.heights[i] for i in range(desc.nlevels))
+        stacks = np.full((nf, rows, desc.vstep), fill, np.uint8)
+        self._ok(self.lib.pislam_b200_build_pyramid(self._h, frames.ctypes.data, W, W * H, nf, int(bool(blur)),
+                                                    C.byref(desc), stacks.ctypes.data, rows * desc.vstep))
+        return stacks
+
+    def extract_frames(self, frames, desc, cap=4096, blur=False):
+        """frames: host uint8 [nframes][H][W] base frames -> list of (kp, level, desc, level_start, n_total)."""
+        frames = np.ascontiguousarray(frames)
+        assert frames.dtype == np.uint8 and frames.ndim == 3
+        nf, H, W = frames.shape
+        assert (W, H) == (desc.widths[0], desc.heights[0]), "base frames must have the size of level 0"
+        lay = record_layout(cap, desc.words)
+        rec = np.zeros(nf * lay["bytes"], np.uint8)
+        st = self.lib.pislam_b200_extract_frames(self._h, frames.ctypes.data, W, W * H, nf, int(bool(blur)),
+                                                 C.byref(desc), cap, rec.ctypes.data)
+        if st != PISLAM_ERR_CAPACITY:
+            self._ok(st)
+        return parse_records(rec, nf, cap, desc.words)
+
+    def extract_frames_ptr(self, frames_ptr, frame_pitch, frame_stride, nframes, desc, cap, records_ptr, blur=False):
+        """Raw-pointer form (host or device memory)."""
+        return self.lib.pislam_b200_extract_frames(self._h, frames_ptr, frame_pitch, frame_stride, nframes,
+                                                   int(bool(blur)), C.byref(desc), cap, records_ptr)
 
     def extract_batch_ptr(self, stacks_ptr, frame_stride, nframes, desc, cap, records_ptr, asynchronous=False):
         """Raw-pointer form (host or device memory, e.g. torch tensors' data_ptr())."""
@@ -394,8 +444,12 @@ class Context:
     def allgather_ptr(self, all_ptr, bytes_per_rank):
         return self.lib.pislam_b200_allgather(self._h, all_ptr, bytes_per_rank)
 
-    def extract_allgather_ptr(self, stacks_ptr, frame_stride, nframes_local, desc, cap, all_records_ptr):
-        return self.lib.pislam_b200_extract_allgather(self._h, stacks_ptr, frame_stride, nframes_local,
+    def extract_allgather_ptr(self, stacks_ptr, frame_stride, nframes_local, desc, cap, all_records_ptr,
+                              slots_per_rank=None):
+        """`slots_per_rank` (same on every rank, default nframes_local) sizes the rank's slot of the gather buffer;
+        a rank may own fewer frames than slots, or none (sharding.shard_frames)."""
+        slots = nframes_local if slots_per_rank is None else slots_per_rank
+        return self.lib.pislam_b200_extract_allgather(self._h, stacks_ptr, frame_stride, nframes_local, slots,
                                                       C.byref(desc), cap, all_records_ptr)
 
 

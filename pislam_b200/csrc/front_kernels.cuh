@@ -70,6 +70,8 @@ struct LevelInfo {
   int xend;           // border + 16*ceil((w-2*border)/16): end of the columns fastDetect writes
   int ntile_cols;
   int piece_base;     // index of the level's first piece
+  int spill;          // fastDetect's last 16-pixel block runs past the row pitch far enough (xend > vstep + border - 1)
+                      // for its flags to land on column border-1 of the NEXT row, which fastExtract reads
 };
 
 struct TileDesc {
@@ -79,6 +81,7 @@ struct TileDesc {
 struct FrontParams {
   const uint8_t* src;  // MODE_LDG: stack of frame 0; MODE_SCOREMAP: `out` map of frame 0 (level row 0)
   unsigned long long frame_stride;
+  unsigned long long frame_bytes;  // readable bytes per frame (rows * vstep <= frame_stride): bounds MODE_LDG's reads
   int vstep, nlevels;
   LevelInfo lv[MAX_LEVELS];
   int border, fast_t;
@@ -363,16 +366,18 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
   } else {
     for (int i = tid; i < SC_H * SC_W / 16; i += NT) reinterpret_cast<uint4*>(s_score)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (MODE == MODE_LDG) {
-      // linear addressing like the reference's img[y][x]; positions outside the frame read as zero
+      // linear addressing like the reference's img[y][x] on a uint8_t(*)[vstep]: a column past the pitch is the
+      // start of the next row (the overrun blocks of Fast.h:36-40,61 read there when w is close to vstep);
+      // positions outside the frame read as zero
       const uint8_t* img = P.src + (size_t)frame * P.frame_stride;
       const long long lo = -(long long)L.row_off * P.vstep;
-      const long long hi = (long long)P.frame_stride - (long long)L.row_off * P.vstep;
+      const long long hi = (long long)P.frame_bytes - (long long)L.row_off * P.vstep;
       const uint8_t* lvl = img + (size_t)L.row_off * P.vstep;
       for (int i = tid; i < PIX_H * PIX_W; i += NT) {
         const int py = i / PIX_W, px = i - py * PIX_W;
         const int x = x0 - 8 + px;
         const long long a = (long long)(y0 - 4 + py) * P.vstep + x;
-        s_pix[i] = (x >= 0 && x < P.vstep && a >= lo && a < hi) ? lvl[a] : (uint8_t)0;
+        s_pix[i] = (a >= lo && a < hi) ? lvl[a] : (uint8_t)0;
       }
     }
     __syncthreads();
@@ -496,6 +501,17 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
       const bool cand = code != 0 && cxp >= 0 && cxp < TW && cyp >= 0 && cyp < TH && x0 + (cxp & ~1) < xs_end &&
                         y0 + (cyp & ~1) < ys_end;
       warp_push(cand, (uint16_t)idx, s_listA, &s_nC);
+    }
+    // The reference's fastDetect writes whole 16-pixel blocks with linear addressing: when the last block of row
+    // y-1 runs past the pitch, its flag for "column vstep + c" is stored at out[y][c] -- and is in fact the FAST
+    // flag of pixel (c, y).  Columns c < border are never rewritten or scored, so for tiny borders (<= 7) the raw
+    // 0xff at column border-1 takes part in the non-max test of the first cell column (Fast.h:36-40,61,231-245).
+    if (MODE == MODE_LDG && L.spill && x0 == B) {
+      for (int ry = tid; ry < SC_H; ry += NT) {
+        const int y = y0 - 1 + ry;
+        if (y >= B + 1 && y <= ys_end && fast9_at(s_pix + (ry + 3) * PIX_W + dxo + 4 + 3, PIX_W, t))
+          s_score[ry * SC_W + 3] = 0xff;
+      }
     }
   }
   __syncthreads();

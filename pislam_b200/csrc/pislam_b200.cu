@@ -131,6 +131,8 @@ struct Geometry {
   int cap = 0;
   bool valid = false;
   int th = TH_BATCH;  // tile height the tables were built for
+  DevBuf tiles;       // the geometry's tile table on the device
+  unsigned long long last_use = 0;
   int ntiles = 0, npieces = 0;
   LevelInfo lv[MAX_LEVELS];
   int piece_base[MAX_LEVELS + 1];
@@ -161,9 +163,25 @@ struct pislam_ctx {
   // literal stages
   DevBuf img, out, kp, desc, aux0, aux1;
   // fused path
-  Geometry geos[2];  // [0] tile height 32 (few tiles), [1] tile height 64 (batches)
-  int gi = 1;        // geometry of the current call
-  DevBuf tiles_th[2], stage, stage_count, piece_cnt, piece_off, stacks, records, hdr;
+  // small LRU of tile / piece tables keyed by (tile height, full descriptor): a caller alternating a few
+  // geometries (levels of different cameras, literal fastExtract per level) re-uses them without any upload
+  static const int kGeoCache = 8;
+  Geometry geos[kGeoCache];
+  Geometry* geo = nullptr;  // geometry of the current call
+  unsigned long long geo_clock = 0;
+  long geo_uploads = 0;
+  DevBuf stage, stage_count, piece_cnt, piece_off, stacks, records, hdr;
+  // pyramid builder (N1): tap tables per geometry (LRU), staging for base frames and the blur passes
+  struct PyrTables {
+    pislam_pyramid_desc d;
+    bool valid = false;
+    unsigned long long last_use = 0;
+    DevBuf taps;
+    PyramidParams proto;  // everything but the pointers / strides of a call
+  };
+  static const int kPyrCache = 4;
+  PyrTables pyr[kPyrCache];
+  DevBuf bases, blur_tmp, blur_out;
   // multi-GPU: the all-gather runs on its own stream so that it overlaps the next batch's kernels
   NcclComm comm = nullptr;
   int nranks = 1, rank = 0;
@@ -179,6 +197,7 @@ struct pislam_ctx {
   static const int kMaxChunks = 8;
   cudaEvent_t ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {};
   int pipeline_chunks = 4;
+  size_t l2_chunk_bytes = 48u << 20;  // device-resident base frames: stack bytes built per chunk (stays in the 126 MB L2)
   bool trim_copies = true;
   void* h_rec = nullptr;  // pinned staging for single-frame results
   size_t h_rec_cap = 0;
@@ -186,7 +205,7 @@ struct pislam_ctx {
   bool profiling = false;
   struct ProfSpan {
     cudaEvent_t a, b;
-    int which;  // 0 front_tile_kernel, 1 order_kernel, 2 orb_kernel
+    int which;  // 0 front_tile_kernel, 1 order_kernel, 2 orb_kernel, 3 pyramid_build_kernel
   };
   std::vector<ProfSpan> spans;
 };
@@ -227,6 +246,18 @@ bool is_device_ptr(const void* p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// The reference addresses img[y][x] linearly on a uint8_t(*)[vstep]; a window is readable iff its first and last
+// byte lie inside the rows the caller handed over.  lo / hi: window extent around (x, y), e.g. -15 / +15.
+bool window_inside(long long x, long long y, int lo, int hi, int vstep, int rows) {
+  const long long first = (y + lo) * vstep + x + lo, last = (y + hi) * vstep + x + hi;
+  return first >= 0 && last < (long long)rows * vstep;
+}
+bool keypoints_inside(const uint32_t* kp, int n, int vstep, int rows) {
+  for (int i = 0; i < n; ++i)
+    if (!window_inside(decode_x(kp[i]), decode_y(kp[i]), -15, 15, vstep, rows)) return false;
+  return true;
+}
+
 int validate_desc(const pislam_pyramid_desc* d, int cap, bool fused) {
   if (!d || d->vstep <= 0 || d->nlevels < 1 || d->nlevels > PISLAM_MAX_LEVELS || cap < 1) return PISLAM_ERR_INVALID_ARG;
   if (d->words < 0 || d->words > 8 || d->bucket_limit < 1 || d->log_bucket_size < 0) return PISLAM_ERR_INVALID_ARG;
@@ -253,19 +284,30 @@ int pick_tile_height(const pislam_ctx* c, const pislam_pyramid_desc* d, int nfra
   return tiles64 * nframes < 4LL * c->num_sms ? TH_SMALL : TH_BATCH;
 }
 
-// Tile + piece tables of a geometry (one cached per tile height); uploads the tile table when the geometry changed.
+// Tile + piece tables of a geometry; cached (LRU) per tile height and descriptor.  A hit costs no upload and no
+// synchronisation; a miss uploads the tile table stream-ordered (the pageable source is consumed before
+// cudaMemcpyAsync returns, and the evicted table's earlier launches precede the copy on the stream).
 int prepare_geometry(pislam_ctx* c, const pislam_pyramid_desc* d, int cap, int nframes) {
   const int TH = pick_tile_height(c, d, nframes);
-  c->gi = TH == TH_BATCH ? 1 : 0;
-  Geometry& g = c->geos[c->gi];
-  DevBuf& tile_buf = c->tiles_th[c->gi];
-  g.th = TH;
-  if (g.valid && same_desc(g.d, *d)) {
-    g.d = *d;
-    g.cap = cap;
+  Geometry* hit = nullptr;
+  Geometry* victim = nullptr;  // a free entry, else the least recently used one
+  for (Geometry& e : c->geos) {
+    if (e.valid && e.th == TH && same_desc(e.d, *d)) {
+      hit = &e;
+      break;
+    }
+    if (!victim || (victim->valid && (!e.valid || e.last_use < victim->last_use))) victim = &e;
+  }
+  if (hit) {
+    hit->d = *d;  // thresholds / bucket_limit / words may differ: they are launch parameters, not table content
+    hit->cap = cap;
+    hit->last_use = ++c->geo_clock;
+    c->geo = hit;
     return PISLAM_OK;
   }
+  Geometry& g = *victim;
   g.valid = false;
+  g.th = TH;
   const int B = d->border;
   const int cb_log = d->log_bucket_size > 0 ? d->log_bucket_size - 1 : 0;
   const int nseg = (TH / 2) >> cb_log;  // segments per tile: cell rows, or bucket bands
@@ -279,6 +321,7 @@ int prepare_geometry(pislam_ctx* c, const pislam_pyramid_desc* d, int cap, int n
     L.row_off = d->row_offsets[l];
     const int iw = L.w - 2 * B, ih = L.h - 2 * B;
     L.xend = B + 16 * ((iw + 15) / 16);
+    L.spill = L.xend > d->vstep + B - 1;
     L.ntile_cols = (iw > 0 && ih > 0) ? (iw + TW - 1) / TW : 0;
     const int ntile_rows = (iw > 0 && ih > 0) ? (ih + TH - 1) / TH : 0;
     L.piece_base = piece;
@@ -302,13 +345,13 @@ int prepare_geometry(pislam_ctx* c, const pislam_pyramid_desc* d, int cap, int n
   g.d = *d;
   g.cap = cap;
   if (g.ntiles > 0) {
-    CK(tile_buf.reserve(tiles.size() * sizeof(TileDesc), false, c->stream));
-    // the table may still be in use by earlier launches on the stream: stream-ordered copy from a
-    // pageable buffer returns once the source has been consumed
-    CK(cudaMemcpyAsync(tile_buf.p, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(g.tiles.reserve(tiles.size() * sizeof(TileDesc), false, c->stream));
+    CK(cudaMemcpyAsync(g.tiles.p, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, c->stream));
+    ++c->geo_uploads;
   }
   g.valid = true;
+  g.last_use = ++c->geo_clock;
+  c->geo = &g;
   return PISLAM_OK;
 }
 
@@ -325,10 +368,11 @@ int make_tensor_map(pislam_ctx* c, CUtensorMap* m, const uint8_t* base, int vste
 }
 
 void fill_front_params(const pislam_ctx* c, FrontParams& P, const uint8_t* src, size_t frame_stride) {
-  const Geometry& g = c->geos[c->gi];
+  const Geometry& g = *c->geo;
   memset(&P, 0, sizeof(P));
   P.src = src;
   P.frame_stride = frame_stride;
+  P.frame_bytes = std::min<unsigned long long>(frame_stride, (unsigned long long)g.rows * g.d.vstep);
   P.vstep = g.d.vstep;
   P.nlevels = g.d.nlevels;
   for (int l = 0; l < g.d.nlevels; ++l) P.lv[l] = g.lv[l];
@@ -339,7 +383,7 @@ void fill_front_params(const pislam_ctx* c, FrontParams& P, const uint8_t* src, 
   P.bucket_limit = g.d.bucket_limit;
   P.cap = g.cap;
   P.npieces = g.npieces;
-  P.tiles = c->tiles_th[c->gi].as<TileDesc>();
+  P.tiles = g.tiles.as<TileDesc>();
   P.stage = c->stage.as<uint32_t>();
   P.stage_count = c->stage_count.as<uint32_t>();
   P.piece_cnt = c->piece_cnt.as<uint32_t>();
@@ -347,7 +391,7 @@ void fill_front_params(const pislam_ctx* c, FrontParams& P, const uint8_t* src, 
 }
 
 int reserve_front_scratch(pislam_ctx* c, int nframes) {
-  const Geometry& g = c->geos[c->gi];
+  const Geometry& g = *c->geo;
   CK(c->stage.reserve((size_t)nframes * g.cap * 4, false, c->stream));
   CK(c->stage_count.reserve((size_t)nframes * 4, true, c->stream));
   CK(c->piece_cnt.reserve((size_t)nframes * std::max(1, g.npieces) * 4, false, c->stream));
@@ -356,7 +400,7 @@ int reserve_front_scratch(pislam_ctx* c, int nframes) {
 }
 
 int launch_order(pislam_ctx* c, int nframes, int words, uint8_t* d_records) {
-  const Geometry& g = c->geos[c->gi];
+  const Geometry& g = *c->geo;
   OrderParams O;
   memset(&O, 0, sizeof(O));
   O.nlevels = g.d.nlevels;
@@ -378,10 +422,12 @@ int launch_order(pislam_ctx* c, int nframes, int words, uint8_t* d_records) {
 // all device pointers; enqueue only
 int enqueue_extract(pislam_ctx* c, const uint8_t* d_stacks, size_t frame_stride, int nframes,
                     const pislam_pyramid_desc* d, int cap, uint8_t* d_records) {
-  if (!d_stacks || !d_records || nframes < 1 || nframes > 65535) return PISLAM_ERR_INVALID_ARG;
+  if (nframes < 0 || nframes > 65535) return PISLAM_ERR_INVALID_ARG;
   CKS(validate_desc(d, cap, true));
+  if (nframes == 0) return PISLAM_OK;  // an empty shard: nothing to launch
+  if (!d_stacks || !d_records) return PISLAM_ERR_INVALID_ARG;
   CKS(prepare_geometry(c, d, cap, nframes));
-  const Geometry& g = c->geos[c->gi];
+  const Geometry& g = *c->geo;
   if (nframes > 1 && frame_stride < (size_t)g.rows * d->vstep) return PISLAM_ERR_INVALID_ARG;
   if (nframes == 1) frame_stride = (size_t)g.rows * d->vstep;
   CKS(reserve_front_scratch(c, nframes));
@@ -456,6 +502,128 @@ int enqueue_extract(pislam_ctx* c, const uint8_t* d_stacks, size_t frame_stride,
     }
     span_end(c);
     CKS(check_launch(c));
+  }
+  return PISLAM_OK;
+}
+
+// ---- pyramid builder ----------------------------------------------------------------
+// taps of oracle/pislam_oracle.h:po_resize_bilinear for one axis
+void resize_taps(int n_out, int n_in, std::vector<uint32_t>& t) {
+  for (int i = 0; i < n_out; ++i) {
+    long long pos = ((long long)(2 * i + 1) * n_in * 128) / n_out - 128;
+    const long long hi = (long long)(n_in - 1) * 256;
+    pos = std::min(std::max(pos, 0LL), hi);
+    const int i0 = (int)(pos >> 8), f = (int)(pos & 255), i1 = std::min(i0 + 1, n_in - 1);
+    t.push_back(pack_tap(i0, i1, f));
+  }
+  while (t.size() % 4) t.push_back(t.back());  // 16-byte loads of four taps never leave the table
+}
+
+int prepare_pyramid_tables(pislam_ctx* c, const pislam_pyramid_desc* d, pislam_ctx::PyrTables** out) {
+  pislam_ctx::PyrTables* victim = nullptr;
+  for (pislam_ctx::PyrTables& e : c->pyr) {
+    if (e.valid && same_desc(e.d, *d)) {
+      e.last_use = ++c->geo_clock;
+      *out = &e;
+      return PISLAM_OK;
+    }
+    if (!victim || (victim->valid && (!e.valid || e.last_use < victim->last_use))) victim = &e;
+  }
+  pislam_ctx::PyrTables& e = *victim;
+  e.valid = false;
+  PyramidParams& P = e.proto;
+  memset(&P, 0, sizeof(P));
+  P.W = d->widths[0];
+  P.H = d->heights[0];
+  P.vstep = d->vstep;
+  P.nlevels = d->nlevels;
+  std::vector<uint32_t> xt, yt;
+  int tile = 0;
+  for (int l = 0; l < d->nlevels; ++l) {
+    P.w[l] = d->widths[l];
+    P.h[l] = d->heights[l];
+    P.row_off[l] = d->row_offsets[l];
+    P.tiles_x[l] = (d->widths[l] + PYR_TW - 1) / PYR_TW;
+    P.tile0[l] = tile;
+    tile += P.tiles_x[l] * ((d->heights[l] + PYR_TH - 1) / PYR_TH);
+    P.xt0[l] = (int)xt.size();
+    resize_taps(d->widths[l], P.W, xt);
+    P.yt0[l] = (int)yt.size();
+    resize_taps(d->heights[l], P.H, yt);
+  }
+  P.tile0[d->nlevels] = tile;
+  CK(e.taps.reserve((xt.size() + yt.size()) * 4, false, c->stream));
+  CK(cudaMemcpyAsync(e.taps.p, xt.data(), xt.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(e.taps.as<uint32_t>() + xt.size(), yt.data(), yt.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  P.xtaps = e.taps.as<uint32_t>();
+  P.ytaps = e.taps.as<uint32_t>() + xt.size();
+  e.d = *d;
+  e.valid = true;
+  e.last_use = ++c->geo_clock;
+  ++c->geo_uploads;
+  *out = &e;
+  return PISLAM_OK;
+}
+
+int validate_frames(const pislam_pyramid_desc* d, int frame_pitch, size_t frame_stride, int nframes, int blur) {
+  if (!d || nframes < 0 || d->nlevels < 1) return PISLAM_ERR_INVALID_ARG;
+  const int W = d->widths[0], H = d->heights[0];
+  if (frame_pitch < W || (nframes > 1 && frame_stride < (size_t)frame_pitch * (H - 1) + W)) return PISLAM_ERR_INVALID_ARG;
+  if (blur && (W < 3 || H < 3)) return PISLAM_ERR_INVALID_ARG;  // reflect-101 borders of the 5x5 blur
+  for (int l = 0; l < d->nlevels; ++l)
+    if (d->widths[l] > 32767 || d->heights[l] > 32767) return PISLAM_ERR_UNSUPPORTED;  // 15-bit tap indices
+  return PISLAM_OK;
+}
+
+// device pointers; enqueue only: [blur passes] + one pyramid_build_kernel launch for the whole batch
+int enqueue_pyramid(pislam_ctx* c, const uint8_t* d_frames, int frame_pitch, size_t frame_stride, int nframes, int blur,
+                    const pislam_pyramid_desc* d, uint8_t* d_stacks, size_t stack_stride, bool zero_padding) {
+  if (nframes == 0) return PISLAM_OK;
+  if (nframes > 65535) return PISLAM_ERR_INVALID_ARG;
+  pislam_ctx::PyrTables* T = nullptr;
+  CKS(prepare_pyramid_tables(c, d, &T));
+  PyramidParams P = T->proto;
+  P.base = d_frames;
+  P.base_pitch = frame_pitch;
+  P.base_stride = frame_stride;
+  if (blur) {
+    // Gaussian.h:48-72 semantics (vertical pass, then horizontal) on every base frame; the levels are resized from
+    // the blurred frame (pitch = width rounded up to 4)
+    const int W = P.W, H = P.H, tpitch = (W + 3) & ~3;
+    const size_t fbytes = (size_t)tpitch * H;
+    CK(c->blur_tmp.reserve(fbytes * nframes + 16, false, c->stream));
+    CK(c->blur_out.reserve(fbytes * nframes + 16, false, c->stream));
+    const dim3 grid(((W + 3) / 4 + 127) / 128, H, nframes);
+    gaussian_vertical_batch_kernel<<<grid, 128, 0, c->stream>>>(d_frames, frame_stride, c->blur_tmp.as<uint8_t>(), fbytes,
+                                                                frame_pitch, tpitch, W, H);
+    CKS(check_launch(c));
+    gaussian_horizontal_batch_kernel<<<grid, 128, 0, c->stream>>>(c->blur_tmp.as<uint8_t>(), fbytes,
+                                                                  c->blur_out.as<uint8_t>(), fbytes, tpitch, tpitch, W, H);
+    CKS(check_launch(c));
+    P.base = c->blur_out.as<uint8_t>();
+    P.base_pitch = tpitch;
+    P.base_stride = fbytes;
+  }
+  P.stacks = d_stacks;
+  P.stack_stride = stack_stride;
+  P.zero_padding = zero_padding ? 1 : 0;
+  span_begin(c, 3);
+  pyramid_build_kernel<<<dim3(P.tile0[P.nlevels], nframes), dim3(32, PYR_TH), 0, c->stream>>>(P);
+  span_end(c);
+  return check_launch(c);
+}
+
+// H2D of base frames [f0, f0+nf) into a tight device layout (pitch dp, stride dp*H)
+int copy_bases_h2d(cudaStream_t st, const uint8_t* host, int pitch, size_t stride, uint8_t* dev, int dp, int W, int H,
+                   int f0, int nf) {
+  const size_t dstride = (size_t)dp * H;
+  if (pitch == dp && stride == dstride) {
+    CK(cudaMemcpyAsync(dev + f0 * dstride, host + f0 * stride, dstride * nf, cudaMemcpyHostToDevice, st));
+  } else if (stride == (size_t)pitch * H) {  // frames are consecutive rows of one tall image
+    CK(cudaMemcpy2DAsync(dev + f0 * dstride, dp, host + f0 * stride, pitch, W, (size_t)H * nf, cudaMemcpyHostToDevice, st));
+  } else {
+    for (int f = f0; f < f0 + nf; ++f)
+      CK(cudaMemcpy2DAsync(dev + f * dstride, dp, host + f * stride, pitch, W, H, cudaMemcpyHostToDevice, st));
   }
   return PISLAM_OK;
 }
@@ -539,6 +707,7 @@ int pislam_b200_create(pislam_ctx** out, int device, size_t max_stack_bytes, int
     if (st != PISLAM_OK) break;
     if (const char* ch = getenv("PISLAM_B200_CHUNKS")) c->pipeline_chunks = std::max(1, std::min(atoi(ch), (int)pislam_ctx::kMaxChunks));
     if (const char* tr = getenv("PISLAM_B200_TRIM")) c->trim_copies = tr[0] != '0';
+    if (const char* l2 = getenv("PISLAM_B200_L2_CHUNK_MB")) c->l2_chunk_bytes = (size_t)std::max(1, atoi(l2)) << 20;
     const char* no_tma = getenv("PISLAM_B200_NO_TMA");
     c->use_tma = !(no_tma && no_tma[0] == '1');
     void* fn = nullptr;
@@ -591,9 +760,14 @@ int pislam_b200_destroy(pislam_ctx* c) {
   if (c->copy_out) cudaStreamSynchronize(c->copy_out);
   if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-  DevBuf* bufs[] = {&c->img, &c->out, &c->kp, &c->desc, &c->aux0, &c->aux1, &c->tiles_th[0], &c->tiles_th[1], &c->stage, &c->stage_count,
+  DevBuf* bufs[] = {&c->img, &c->out, &c->kp, &c->desc, &c->aux0, &c->aux1, &c->stage, &c->stage_count,
                     &c->piece_cnt, &c->piece_off, &c->stacks, &c->records, &c->hdr};
   for (DevBuf* b : bufs) b->release();
+  for (Geometry& e : c->geos) e.tiles.release();
+  for (pislam_ctx::PyrTables& e : c->pyr) e.taps.release();
+  c->bases.release();
+  c->blur_tmp.release();
+  c->blur_out.release();
   if (c->d_brief) cudaFree(c->d_brief);
   if (c->h_rec) cudaFreeHost(c->h_rec);
   if (c->d_brief48) cudaFree(c->d_brief48);
@@ -636,6 +810,7 @@ int pislam_b200_synchronize(pislam_ctx* c) {
 }
 
 long pislam_b200_launch_count(pislam_ctx* c) { return c ? c->launches : 0; }
+long pislam_b200_geometry_uploads(pislam_ctx* c) { return c ? c->geo_uploads : 0; }
 
 int pislam_b200_set_tma(pislam_ctx* c, int enable) {
   if (!c) return PISLAM_ERR_INVALID_ARG;
@@ -649,11 +824,11 @@ int pislam_b200_set_profiling(pislam_ctx* c, int enable) {
   return PISLAM_OK;
 }
 
-int pislam_b200_kernel_times(pislam_ctx* c, double ms[3], long count[3]) {
+int pislam_b200_kernel_times(pislam_ctx* c, double ms[4], long count[4]) {
   if (!c || !ms || !count) return PISLAM_ERR_INVALID_ARG;
   CKS(set_device(c));
   CK(cudaStreamSynchronize(c->stream));
-  for (int k = 0; k < 3; ++k) {
+  for (int k = 0; k < 4; ++k) {
     ms[k] = 0.0;
     count[k] = 0;
   }
@@ -752,10 +927,10 @@ int pislam_b200_fast_extract(pislam_ctx* c, const uint8_t* out, int vstep, int b
   fill_front_params(c, P, c->out.as<uint8_t>(), bytes);
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
-  if (c->geos[c->gi].th == TH_BATCH)
-    front_tile_kernel<MODE_SCOREMAP, TH_BATCH><<<dim3(c->geos[c->gi].ntiles, 1), NT, 0, c->stream>>>(P, tmap);
+  if (c->geo->th == TH_BATCH)
+    front_tile_kernel<MODE_SCOREMAP, TH_BATCH><<<dim3(c->geo->ntiles, 1), NT, 0, c->stream>>>(P, tmap);
   else
-    front_tile_kernel<MODE_SCOREMAP, TH_SMALL><<<dim3(c->geos[c->gi].ntiles, 1), NT, 0, c->stream>>>(P, tmap);
+    front_tile_kernel<MODE_SCOREMAP, TH_SMALL><<<dim3(c->geo->ntiles, 1), NT, 0, c->stream>>>(P, tmap);
   CKS(check_launch(c));
   CKS(launch_order(c, 1, 0, c->records.as<uint8_t>()));
   uint32_t header[2];
@@ -772,6 +947,8 @@ int pislam_b200_harris_score_sobel(pislam_ctx* c, const uint8_t* img, int vstep,
                                    const int* ys, int npts, int32_t threshold, uint8_t* scores) {
   if (!c || !img || vstep < 1 || rows < 1 || npts < 0 || (npts && (!xs || !ys || !scores))) return PISLAM_ERR_INVALID_ARG;
   if (npts == 0) return PISLAM_OK;
+  for (int i = 0; i < npts; ++i)  // the 8x8 window rows y-3..y+4, columns x-3..x+4 (Harris.h:103-111)
+    if (!window_inside(xs[i], ys[i], -3, 4, vstep, rows)) return PISLAM_ERR_INVALID_ARG;
   CKS(set_device(c));
   const size_t bytes = (size_t)rows * vstep;
   CK(c->img.reserve(bytes, false, c->stream));
@@ -794,6 +971,7 @@ int pislam_b200_orb_centroids(pislam_ctx* c, const uint8_t* img, int vstep, int 
                               int32_t* centroids) {
   if (!c || !img || vstep < 1 || rows < 1 || n < 0 || (n && (!kp || !centroids))) return PISLAM_ERR_INVALID_ARG;
   if (n == 0) return PISLAM_OK;
+  if (!keypoints_inside(kp, n, vstep, rows)) return PISLAM_ERR_INVALID_ARG;  // 31x31 patch outside the image
   CKS(set_device(c));
   const size_t bytes = (size_t)rows * vstep;
   const int size = (2 * n + 7) & ~7;  // Orb.h:113-114
@@ -829,7 +1007,7 @@ int pislam_b200_brief_describe(pislam_ctx* c, const uint8_t* img, int vstep, int
                                int words, uint32_t* desc) {
   if (!c || !img || !desc || vstep < 1 || rows < 1 || words < 1 || words > 8) return PISLAM_ERR_INVALID_ARG;
   if (rot < 0 || rot >= 30) return PISLAM_OK;  // Brief.h:641-732: descriptor untouched
-  if (x < 15 || y < 15 || y + 15 >= rows) return PISLAM_ERR_INVALID_ARG;
+  if (!window_inside(x, y, -15, 15, vstep, rows)) return PISLAM_ERR_INVALID_ARG;
   CKS(set_device(c));
   const size_t bytes = (size_t)rows * vstep;
   CK(c->img.reserve(bytes, false, c->stream));
@@ -848,6 +1026,7 @@ int pislam_b200_orb_compute(pislam_ctx* c, const uint8_t* img, int vstep, int ro
   if (!c || !img || vstep < 1 || rows < 1 || n < 0 || words < 1 || words > 8 || (n && (!kp || !desc)))
     return PISLAM_ERR_INVALID_ARG;
   if (n == 0) return PISLAM_OK;
+  if (!keypoints_inside(kp, n, vstep, rows)) return PISLAM_ERR_INVALID_ARG;  // 31x31 patch outside the image
   CKS(set_device(c));
   const size_t bytes = (size_t)rows * vstep;
   CK(c->img.reserve(bytes, false, c->stream));
@@ -945,57 +1124,98 @@ int pislam_b200_extract_batch_async(pislam_ctx* c, const uint8_t* d_stacks, size
   return enqueue_extract(c, d_stacks, frame_stride, nframes, d, cap, static_cast<uint8_t*>(d_records));
 }
 
-int pislam_b200_extract_batch(pislam_ctx* c, const uint8_t* stacks, size_t frame_stride, int nframes,
-                              const pislam_pyramid_desc* d, int cap, void* records) {
-  if (!c || !stacks || !records || nframes < 1) return PISLAM_ERR_INVALID_ARG;
+namespace {
+// What a fused call starts from: stacked pyramids (the reference's input, README.md:56-83) or base frames that the
+// pyramid builder expands on the device first.  Host or device memory.
+struct FrameSource {
+  const uint8_t* p;
+  bool base;      // base frames (pitch / blur apply) instead of stacks
+  int pitch;      // base frames: row pitch
+  size_t stride;  // bytes between frames
+  int blur;       // base frames: Gaussian.h:48-72 blur before resizing
+};
+
+// The whole fused path for a batch, blocking.  Host sources are pipelined in chunks over three streams:
+// copy_in (H2D of chunk i+1) || stream (kernels of chunk i) || copy_out (D2H of the records of chunk i-1).
+int extract_pipeline(pislam_ctx* c, const FrameSource& src, int nframes, const pislam_pyramid_desc* d, int cap,
+                     void* records) {
+  if (!c || !src.p || !records || nframes < 1) return PISLAM_ERR_INVALID_ARG;
   CKS(set_device(c));
   CKS(validate_desc(d, cap, true));
   long long rows = 0;
   for (int l = 0; l < d->nlevels; ++l) rows = std::max<long long>(rows, (long long)d->row_offsets[l] + d->heights[l]);
   const size_t frame_bytes = (size_t)rows * d->vstep;
-  if (nframes == 1) frame_stride = frame_bytes;
-  if (frame_stride < frame_bytes) return PISLAM_ERR_INVALID_ARG;
+  size_t stack_stride = src.base ? frame_bytes : (nframes == 1 ? frame_bytes : src.stride);
+  if (src.base) CKS(validate_frames(d, src.pitch, src.stride, nframes, src.blur));
+  else if (stack_stride < frame_bytes) return PISLAM_ERR_INVALID_ARG;
   const size_t rec_bytes = RecordLayout::make(cap, d->words).bytes;
-  const bool stacks_on_host = !is_device_ptr(stacks);
+  const bool src_on_host = !is_device_ptr(src.p);
   const bool rec_on_host = !is_device_ptr(records);
   uint8_t* d_records = static_cast<uint8_t*>(records);
   if (rec_on_host) {
     CK(c->records.reserve(rec_bytes * nframes, false, c->stream));
     d_records = c->records.as<uint8_t>();
   }
-  if (stacks_on_host) {
-    // chunked pipeline: copy_in(H2D i+1) || stream(kernels i) || copy_out(D2H i-1)
-    const size_t total = (size_t)(nframes - 1) * frame_stride + frame_bytes;
-    CK(c->stacks.reserve(total, false, c->stream));
-    uint8_t* d_stacks = c->stacks.as<uint8_t>();
-    const int nchunks = std::max(1, std::min(c->pipeline_chunks, nframes));
-    const int per = (nframes + nchunks - 1) / nchunks;
-    CKS(prepare_geometry(c, d, cap, per));
-    CKS(reserve_front_scratch(c, per));
-    // earlier work on the ctx stream may still read the staging buffer
+  if (!src.base && !src_on_host) {
+    CKS(enqueue_extract(c, src.p, stack_stride, nframes, d, cap, d_records));
+    if (rec_on_host) CK(cudaMemcpyAsync(records, d_records, rec_bytes * nframes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  } else {
+    // chunks: a host source is cut for the copy/compute overlap; device-resident base frames are cut so that a
+    // chunk's freshly built stacks are still in L2 when the detector and the descriptor kernel read them
+    int per = nframes;
+    if (src_on_host) per = (nframes + std::min(c->pipeline_chunks, nframes) - 1) / std::min(c->pipeline_chunks, nframes);
+    else per = (int)std::max<long long>(1, std::min<long long>(nframes, (long long)c->l2_chunk_bytes / (long long)frame_bytes));
+    uint8_t* d_stacks = nullptr;
+    const uint8_t* d_bases = src.p;
+    int bp = src.pitch;
+    size_t bstride = src.stride;
+    if (src.base) {
+      // the stacks of ALL chunks stay allocated (the descriptor kernel of a chunk may still run while the next
+      // chunk's pyramid is being built); padding columns are never read by the detector, so they are not cleared
+      CK(c->stacks.reserve(frame_bytes * nframes, false, c->stream));
+      d_stacks = c->stacks.as<uint8_t>();
+      if (src_on_host) {
+        bp = (d->widths[0] + 15) & ~15;
+        bstride = (size_t)bp * d->heights[0];
+        CK(c->bases.reserve(bstride * nframes, false, c->stream));
+        d_bases = c->bases.as<uint8_t>();
+      }
+    } else {
+      const size_t total = (size_t)(nframes - 1) * stack_stride + frame_bytes;
+      CK(c->stacks.reserve(total, false, c->stream));
+      d_stacks = c->stacks.as<uint8_t>();
+    }
+    // earlier work on the ctx stream may still read the staging buffers
     CK(cudaEventRecord(c->ev_k[0], c->stream));
     CK(cudaStreamWaitEvent(c->copy_in, c->ev_k[0], 0));
     int i = 0;
     for (int f0 = 0; f0 < nframes; f0 += per, ++i) {
       const int nf = std::min(per, nframes - f0);
-      CKS(copy_frames_h2d(c, c->copy_in, stacks, d_stacks, frame_stride, frame_bytes, f0, nf, d));
-      CK(cudaEventRecord(c->ev_in[i], c->copy_in));
-      CK(cudaStreamWaitEvent(c->stream, c->ev_in[i], 0));
-      CKS(enqueue_extract(c, d_stacks + (size_t)f0 * frame_stride, frame_stride, nf, d, cap,
+      const int e = i % pislam_ctx::kMaxChunks;
+      if (src_on_host) {
+        if (src.base)
+          CKS(copy_bases_h2d(c->copy_in, src.p, src.pitch, src.stride, c->bases.as<uint8_t>(), bp, d->widths[0],
+                             d->heights[0], f0, nf));
+        else
+          CKS(copy_frames_h2d(c, c->copy_in, src.p, d_stacks, stack_stride, frame_bytes, f0, nf, d));
+        CK(cudaEventRecord(c->ev_in[e], c->copy_in));
+        CK(cudaStreamWaitEvent(c->stream, c->ev_in[e], 0));
+      }
+      if (src.base)
+        CKS(enqueue_pyramid(c, d_bases + (size_t)f0 * bstride, bp, bstride, nf, src.blur, d,
+                            d_stacks + (size_t)f0 * stack_stride, stack_stride, false));
+      CKS(enqueue_extract(c, d_stacks + (size_t)f0 * stack_stride, stack_stride, nf, d, cap,
                           d_records + (size_t)f0 * rec_bytes));
       if (rec_on_host) {
-        CK(cudaEventRecord(c->ev_k[i], c->stream));
-        CK(cudaStreamWaitEvent(c->copy_out, c->ev_k[i], 0));
+        CK(cudaEventRecord(c->ev_k[e], c->stream));
+        CK(cudaStreamWaitEvent(c->copy_out, c->ev_k[e], 0));
         CK(cudaMemcpyAsync(static_cast<uint8_t*>(records) + (size_t)f0 * rec_bytes, d_records + (size_t)f0 * rec_bytes,
                            rec_bytes * nf, cudaMemcpyDeviceToHost, c->copy_out));
       }
     }
     CK(cudaStreamSynchronize(c->stream));
     if (rec_on_host) CK(cudaStreamSynchronize(c->copy_out));
-  } else {
-    CKS(enqueue_extract(c, stacks, frame_stride, nframes, d, cap, d_records));
-    if (rec_on_host) CK(cudaMemcpyAsync(records, d_records, rec_bytes * nframes, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
   }
   if (rec_on_host) {
     const uint8_t* r = static_cast<const uint8_t*>(records);
@@ -1006,6 +1226,58 @@ int pislam_b200_extract_batch(pislam_ctx* c, const uint8_t* stacks, size_t frame
     return PISLAM_OK;
   }
   return check_capacity(c, d_records, nframes, rec_bytes);
+}
+}  // namespace
+
+int pislam_b200_extract_batch(pislam_ctx* c, const uint8_t* stacks, size_t frame_stride, int nframes,
+                              const pislam_pyramid_desc* d, int cap, void* records) {
+  const FrameSource src = {stacks, false, 0, frame_stride, 0};
+  return extract_pipeline(c, src, nframes, d, cap, records);
+}
+
+int pislam_b200_extract_frames(pislam_ctx* c, const uint8_t* frames, int frame_pitch, size_t frame_stride, int nframes,
+                               int blur, const pislam_pyramid_desc* d, int cap, void* records) {
+  const FrameSource src = {frames, true, frame_pitch, frame_stride, blur};
+  return extract_pipeline(c, src, nframes, d, cap, records);
+}
+
+int pislam_b200_build_pyramid(pislam_ctx* c, const uint8_t* frames, int frame_pitch, size_t frame_stride, int nframes,
+                              int blur, const pislam_pyramid_desc* d, uint8_t* stacks, size_t stack_stride) {
+  if (!c || !frames || !stacks || nframes < 1) return PISLAM_ERR_INVALID_ARG;
+  CKS(set_device(c));
+  CKS(validate_desc(d, 1, false));
+  CKS(validate_frames(d, frame_pitch, frame_stride, nframes, blur));
+  long long rows = 0;
+  for (int l = 0; l < d->nlevels; ++l) rows = std::max<long long>(rows, (long long)d->row_offsets[l] + d->heights[l]);
+  const size_t frame_bytes = (size_t)rows * d->vstep;
+  if (nframes == 1) stack_stride = frame_bytes;
+  if (stack_stride < frame_bytes) return PISLAM_ERR_INVALID_ARG;
+  const uint8_t* d_frames = frames;
+  int bp = frame_pitch;
+  size_t bstride = frame_stride;
+  if (!is_device_ptr(frames)) {
+    bp = (d->widths[0] + 15) & ~15;
+    bstride = (size_t)bp * d->heights[0];
+    CK(c->bases.reserve(bstride * nframes, false, c->stream));
+    CKS(copy_bases_h2d(c->stream, frames, frame_pitch, frame_stride, c->bases.as<uint8_t>(), bp, d->widths[0],
+                       d->heights[0], 0, nframes));
+    d_frames = c->bases.as<uint8_t>();
+  }
+  const bool out_on_host = !is_device_ptr(stacks);
+  uint8_t* d_stacks = stacks;
+  const size_t total = (size_t)(nframes - 1) * stack_stride + frame_bytes;
+  if (out_on_host) {
+    CK(c->stacks.reserve(total, false, c->stream));
+    d_stacks = c->stacks.as<uint8_t>();
+    // rows of the stack that belong to no level come back as the caller left them
+    CK(cudaMemcpyAsync(d_stacks, stacks, total, cudaMemcpyHostToDevice, c->stream));
+  }
+  CKS(enqueue_pyramid(c, d_frames, bp, bstride, nframes, blur, d, d_stacks, stack_stride, true));
+  if (out_on_host) {
+    CK(cudaMemcpyAsync(stacks, d_stacks, total, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return PISLAM_OK;
 }
 
 int pislam_b200_extract_pyramid(pislam_ctx* c, const uint8_t* stack, const pislam_pyramid_desc* d, uint32_t* kp,
@@ -1082,8 +1354,12 @@ int pislam_b200_comm_init(pislam_ctx* c, int nranks, int rank, const void* id128
   CKS(set_device(c));
   NcclUid id;
   memcpy(&id, id128, sizeof(id));
+  if (c->comm) CKS(pislam_b200_comm_destroy(c));  // a second init replaces the communicator (no leak)
   const int r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
-  if (r != 0) return PISLAM_ERR_NCCL - r;
+  if (r != 0) {
+    c->comm = nullptr;
+    return PISLAM_ERR_NCCL - r;
+  }
   c->nranks = nranks;
   c->rank = rank;
   return PISLAM_OK;
@@ -1104,28 +1380,47 @@ int pislam_b200_comm_destroy(pislam_ctx* c) {
 }
 
 int pislam_b200_extract_allgather(pislam_ctx* c, const uint8_t* d_stacks, size_t frame_stride, int nframes_local,
-                                  const pislam_pyramid_desc* d, int cap, void* d_all_records) {
-  if (!c || !d_all_records || !d) return PISLAM_ERR_INVALID_ARG;
+                                  int slots_per_rank, const pislam_pyramid_desc* d, int cap, void* d_all_records) {
+  if (!c || !d_all_records || !d || slots_per_rank < 1 || nframes_local < 0 || nframes_local > slots_per_rank ||
+      (nframes_local > 0 && !d_stacks))
+    return PISLAM_ERR_INVALID_ARG;
   if (!c->comm) return PISLAM_ERR_NCCL;
   CKS(set_device(c));
+  // everything that can fail on this rank alone is checked BEFORE any work is enqueued: once the kernels are
+  // in flight the collective is issued unconditionally, so no peer is left waiting in ncclAllGather
+  CKS(validate_desc(d, cap, true));
   const size_t rec_bytes = RecordLayout::make(cap, d->words).bytes;
-  const size_t slot = rec_bytes * (size_t)nframes_local;
+  const size_t slot = rec_bytes * (size_t)slots_per_rank;
   // the kernels write this rank's records straight into its slot of the gather buffer (in-place gather)
   uint8_t* mine = static_cast<uint8_t*>(d_all_records) + slot * (size_t)c->rank;
   // a gather that is still filling this buffer must finish before the kernels write into it again; with two
   // alternating buffers the previous gather (other buffer) keeps running under this batch's kernels
+  pislam_ctx::GatherSlot& g = c->gathers[c->gather_turn];
+  bool known = false;
   for (int i = 0; i < 2; ++i)
-    if (c->gathers[i].ptr == d_all_records) CK(cudaStreamWaitEvent(c->stream, c->gathers[i].done, 0));
-  CKS(enqueue_extract(c, d_stacks, frame_stride, nframes_local, d, cap, mine));
-  CK(cudaEventRecord(c->ev_extract, c->stream));
-  CK(cudaStreamWaitEvent(c->comm_stream, c->ev_extract, 0));
+    if (c->gathers[i].ptr == d_all_records) {
+      CK(cudaStreamWaitEvent(c->stream, c->gathers[i].done, 0));
+      known = true;
+    }
+  // a third buffer evicts the older entry: from then on nothing remembers that entry's gather, so order this
+  // call (and through the stream everything later) behind it
+  if (!known && g.ptr) CK(cudaStreamWaitEvent(c->stream, g.done, 0));
+  int st = enqueue_extract(c, d_stacks, frame_stride, nframes_local, d, cap, mine);
+  // a ragged shard leaves trailing slots unused: their headers read "no keypoints" (n = n_total = 0, level starts 0)
+  if (st == PISLAM_OK && nframes_local < slots_per_rank) {
+    cudaError_t e = cudaMemset2DAsync(mine + rec_bytes * (size_t)nframes_local, rec_bytes, 0, REC_HEADER_WORDS * 4,
+                                      (size_t)(slots_per_rank - nframes_local), c->stream);
+    if (e != cudaSuccess) st = -(int)e;
+  }
+  cudaError_t e = cudaEventRecord(c->ev_extract, c->stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(c->comm_stream, c->ev_extract, 0);
+  if (e != cudaSuccess && st == PISLAM_OK) st = -(int)e;
   const int r = g_nccl.AllGather(mine, d_all_records, slot, /*ncclInt8*/ 0, c->comm, c->comm_stream);
   if (r != 0) return PISLAM_ERR_NCCL - r;
-  pislam_ctx::GatherSlot& g = c->gathers[c->gather_turn];
   c->gather_turn ^= 1;
   g.ptr = d_all_records;
   CK(cudaEventRecord(g.done, c->comm_stream));
-  return PISLAM_OK;
+  return st;
 }
 
 int pislam_b200_join(pislam_ctx* c) {

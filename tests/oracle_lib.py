@@ -153,6 +153,27 @@ class Oracle(_Lib):
         self.lib.po_gaussian5x5.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int]
         self.lib.po_gaussian5x5(_p(img, u8p), _p(out, u8p), img.shape[1], width, height)
 
+    def resize_bilinear(self, src, w, h):
+        """src: 2-D uint8 (any pitch) -> h x w uint8 (the pyramid builder's resize, oracle/pislam_oracle.h)."""
+        self.lib.po_resize_bilinear.argtypes = [u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int]
+        src = np.ascontiguousarray(src)
+        dst = np.zeros((h, w), np.uint8)
+        self.lib.po_resize_bilinear(_p(src, u8p), src.shape[1], src.shape[1], src.shape[0], _p(dst, u8p), w, w, h)
+        return dst
+
+    def build_pyramid(self, base, layout, blur=False):
+        """base: H x W uint8 -> stacked pyramid [layout.rows][layout.vstep] (levels resized from the base)."""
+        self.lib.po_build_pyramid.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, intp, intp, intp, u8p]
+        base = np.ascontiguousarray(base)
+        assert base.shape == (layout.heights[0], layout.widths[0])
+        w = np.asarray(layout.widths, np.int32)
+        h = np.asarray(layout.heights, np.int32)
+        r = np.asarray(layout.row_offsets, np.int32)
+        stack = np.full((layout.rows, layout.vstep), 0xEE, np.uint8)
+        self.lib.po_build_pyramid(_p(base, u8p), base.shape[1], int(bool(blur)), layout.vstep, layout.nlevels,
+                                  _p(w, intp), _p(h, intp), _p(r, intp), _p(stack, u8p))
+        return stack
+
     def angle_bin(self, m10, m01):
         return int(self.lib.po_angle_bin(int(m10), int(m01)))
 
@@ -175,10 +196,11 @@ class Oracle(_Lib):
         kp = np.zeros(cap, np.uint32)
         lv = np.zeros(cap, np.uint8)
         desc = np.zeros(cap * words, np.uint32)
+        # words == 0: keypoints only (no descriptor pass, so borders < 16 are fine)
         n = self.lib.po_extract_pyramid(_p(stack, u8p), stack.shape[1], nl, _p(w, intp), _p(h, intp), _p(r, intp),
                                         border, fast_threshold, harris_threshold, log_bucket, bucket_limit,
                                         words, int(stacked_y), _p(scratch, u8p), _p(kp, u32p), _p(lv, u8p),
-                                        _p(desc, u32p), cap)
+                                        _p(desc, u32p) if words else None, cap)
         assert n >= 0, n
         res = (kp[:n].copy(), lv[:n].copy(), desc[:n * words].reshape(n, words).copy())
         return res + (scratch,) if want_out else res

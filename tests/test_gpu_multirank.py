@@ -1,8 +1,11 @@
-"""Two-GPU check of the path's only collective: every rank extracts its shard of frames
-with pislam_b200_extract_allgather (records written in place into the gather buffer, one ncclAllGather on the
-second stream) and EVERY rank must end up with all frames' records, bit-exact against the oracle; the same through
-pislam_b200_extract_batch + pislam_b200_allgather, and with two alternating gather buffers (the overlapped form
-bench.py times).  Needs >= 2 B200s (skipped otherwise): `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multirank.py -m gpu`."""
+"""Multi-GPU check of the path's only exchange step: every rank extracts its shard of frames
+with pislam_b200_extract_allgather (records written in place into the gather buffer, one collective on the second
+stream) and EVERY rank must end up with all frames' records, bit-exact against the oracle.  Covered: even shards,
+ragged shards (5 frames over 2 ranks, 11 over 8) and empty shards (1 frame over 2 ranks, 3 over 8: trailing ranks own
+nothing and still take part), alternating gather buffers (the overlapped form bench.py times), the same buffer twice
+in a row, a third buffer (eviction of the tracked gather), and pislam_b200_extract_batch + the stand-alone
+pislam_b200_allgather.  Runs at 2 ranks and at 8 ranks; each is skipped when the box has fewer GPUs:
+`gpurun --gpus 8 -- python -m pytest tests/test_gpu_multirank.py -m gpu`."""
 import os
 import sys
 
@@ -12,10 +15,10 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
-CAP, WORDS, PER_RANK = 2048, 8, 3
+CAP, WORDS = 2048, 8
 
 
-def worker(rank, world, port, out):
+def worker(rank, world, port, frame_counts, out):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -27,64 +30,90 @@ def worker(rank, world, port, out):
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", rank=rank, world_size=world)  # host-side rendezvous only
-    nframes = world * PER_RANK
-    start, count = sharding.shard_frames(nframes, world, rank)
-    stacks = np.stack([synthetic_stack(VGA, 500 + f) for f in range(start, start + count)])
-    d_stacks = torch.from_numpy(stacks).cuda()
     desc = api.make_desc(VGA, log_bucket=4, bucket_limit=3, words=WORDS)
     rec_bytes = api.record_layout(CAP, WORDS)["bytes"]
     ctx = api.Context(rank)
     uid = [api.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     ctx.comm_init(world, rank, uid[0])
-    bufs = [torch.zeros(world * PER_RANK * rec_bytes, dtype=torch.uint8, device="cuda") for _ in range(2)]
-    ok = True
     oracle = oracle_lib.Oracle()
-    want = [oracle.extract_pyramid(synthetic_stack(VGA, 500 + f), VGA.widths, VGA.heights, VGA.row_offsets,
-                                   log_bucket=4, bucket_limit=3) for f in range(nframes)]
+    nmax = max(frame_counts)
+    all_stacks = [synthetic_stack(VGA, 500 + f) for f in range(nmax)]
+    want = [oracle.extract_pyramid(s, VGA.widths, VGA.heights, VGA.row_offsets, log_bucket=4, bucket_limit=3)
+            for s in all_stacks]
+    failures = []
 
-    def check(buf):
-        good = True
-        recs = api.parse_records(buf.cpu().numpy(), world * PER_RANK, CAP, WORDS)
-        for f, (r, s) in enumerate(sharding.gathered_index(nframes, world)):
-            kp, lv, dsc, _, n_total = recs[r * PER_RANK + s]
-            good &= np.array_equal(kp, want[f][0]) and np.array_equal(lv, want[f][1]) and np.array_equal(dsc, want[f][2])
-        return good
+    for nframes in frame_counts:
+        per = sharding.frames_per_rank(nframes, world)
+        start, count = sharding.shard_frames(nframes, world, rank)
+        stacks = np.stack(all_stacks[start:start + count]) if count else np.zeros((1, VGA.rows, VGA.vstep), np.uint8)
+        d_stacks = torch.from_numpy(stacks).cuda()
+        bufs = [torch.full((world * per * rec_bytes,), 0xA5, dtype=torch.uint8, device="cuda") for _ in range(3)]
 
-    # (1) fused extract + gather, alternating buffers, several rounds back to back (overlapped gathers)
-    for it in range(6):
-        st = ctx.extract_allgather_ptr(d_stacks.data_ptr(), VGA.stack_bytes, count, desc, CAP, bufs[it & 1].data_ptr())
-        ok &= st == 0
-    ctx.synchronize()
-    ok &= check(bufs[0]) and check(bufs[1])
-    # (2) the same buffer twice in a row (the second extraction must wait for the first gather)
-    bufs[0].zero_()
-    for it in range(2):
-        ok &= ctx.extract_allgather_ptr(d_stacks.data_ptr(), VGA.stack_bytes, count, desc, CAP, bufs[0].data_ptr()) == 0
-    ctx.synchronize()
-    ok &= check(bufs[0])
-    # (3) extract_batch into this rank's slot, then the stand-alone in-place all-gather
-    bufs[1].zero_()
-    slot = bufs[1][rank * PER_RANK * rec_bytes:(rank + 1) * PER_RANK * rec_bytes]
-    ok &= ctx.extract_batch_ptr(stacks.ctypes.data, VGA.stack_bytes, count, desc, CAP, slot.data_ptr()) == 0
-    ok &= ctx.allgather_ptr(bufs[1].data_ptr(), PER_RANK * rec_bytes) == 0
-    ctx.synchronize()
-    ok &= check(bufs[1])
-    out[rank] = bool(ok)
+        def check(buf, what):
+            recs = api.parse_records(buf.cpu().numpy(), world * per, CAP, WORDS)
+            good = True
+            seen = set()
+            for f, (r, s) in enumerate(sharding.gathered_index(nframes, world)):
+                kp, lv, dsc, _, n_total = recs[r * per + s]
+                seen.add(r * per + s)
+                good &= (n_total == len(want[f][0]) and np.array_equal(kp, want[f][0]) and
+                         np.array_equal(lv, want[f][1]) and np.array_equal(dsc, want[f][2]))
+            for i in set(range(world * per)) - seen:  # unused slots of ragged / empty shards read "no keypoints"
+                good &= len(recs[i][0]) == 0 and recs[i][4] == 0
+            if not good:
+                failures.append("%d frames: %s" % (nframes, what))
+
+        def extract(buf):
+            st = ctx.extract_allgather_ptr(d_stacks.data_ptr() if count else 0, VGA.stack_bytes, count, desc, CAP,
+                                           buf.data_ptr(), slots_per_rank=per)
+            if st != 0:
+                failures.append("%d frames: extract_allgather status %d" % (nframes, st))
+
+        # (1) alternating buffers, several rounds back to back (overlapped gathers)
+        for it in range(6):
+            extract(bufs[it & 1])
+        ctx.synchronize()
+        check(bufs[0], "alternating buffer 0")
+        check(bufs[1], "alternating buffer 1")
+        # (2) the same buffer twice in a row (the second extraction must wait for the first gather), then a third
+        # buffer (evicts the older tracked gather) and back
+        bufs[0].fill_(0x5A)
+        for b in (0, 0, 2, 1, 0):
+            extract(bufs[b])
+        ctx.synchronize()
+        for b in range(3):
+            check(bufs[b], "buffer %d after the 0,0,2,1,0 sequence" % b)
+        # (3) extract_batch into this rank's slot, then the stand-alone in-place all-gather (even shards only:
+        # pislam_b200_allgather moves whole slots and knows nothing about unused ones)
+        if nframes == world * per:
+            bufs[1].zero_()
+            slot = bufs[1][rank * per * rec_bytes:(rank + 1) * per * rec_bytes]
+            st = ctx.extract_batch_ptr(stacks.ctypes.data, VGA.stack_bytes, count, desc, CAP, slot.data_ptr())
+            st2 = ctx.allgather_ptr(bufs[1].data_ptr(), per * rec_bytes)
+            ctx.synchronize()
+            if st != 0 or st2 != 0:
+                failures.append("%d frames: extract_batch %d / allgather %d" % (nframes, st, st2))
+            check(bufs[1], "extract_batch + allgather")
+        dist.barrier()
+        del bufs, d_stacks
+    out[rank] = failures
     dist.barrier()
     ctx.comm_destroy()
     ctx.close()
     dist.destroy_process_group()
 
 
-def test_two_gpu_allgather_matches_oracle():
+@pytest.mark.parametrize("world", [2, 8])
+def test_multi_gpu_allgather_matches_oracle(world):
     import torch
     import torch.multiprocessing as mp
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
-    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    # even / ragged / (mostly) empty shards
+    frame_counts = [6, 5, 1] if world == 2 else [16, 11, 3]
     mgr = mp.Manager()
     out = mgr.dict()
-    port = 29600 + (os.getpid() % 2000)
-    mp.spawn(worker, args=(world, port, out), nprocs=world, join=True)
-    assert dict(out) == {0: True, 1: True}
+    port = 29600 + (os.getpid() % 2000) + world
+    mp.spawn(worker, args=(world, port, frame_counts, out), nprocs=world, join=True)
+    assert dict(out) == {r: [] for r in range(world)}

@@ -346,6 +346,84 @@ def test_fused_keypoints_only_and_words(ctx, oracle):
             assert_same(desc, odesc, "words=%d descriptors" % words)
 
 
+@pytest.mark.parametrize("tma", [True, False])
+@pytest.mark.parametrize("border", [5, 8, 9, 12])
+def test_fused_keypoints_only_small_borders(ctx, oracle, border, tma):
+    """Keypoints-only extraction (words = 0) admits borders 5..15: borders that are multiples of 4 stage the tiles
+    by TMA, the others by plain loads (and `tma=False` forces plain loads for all of them).  Synthetic, ragged and
+    noise levels, plain and bucketed."""
+    rng = np.random.Generator(np.random.PCG64(100 + border))
+    lay = pyramid_layout(320, 240, nlevels=3)
+    noise = noise_stack(lay, 50 + border)
+    dims = [(208, 61), (173, 64), (2 * border + 1, 40), (139, 2 * border + 2), (50, 31)]
+    offs, r = [], 0
+    for w, h in dims:
+        offs.append(r)
+        r += h
+    rag = PyramidLayout(208, [w for w, h in dims], [h for w, h in dims], offs)
+    rstack = np.zeros((r, 208), np.uint8)
+    for (w, h), o in zip(dims, offs):
+        coarse = rng.integers(0, 256, size=(h // 5 + 2, w // 5 + 2), dtype=np.uint8)
+        rstack[o:o + h, :w] = np.kron(coarse, np.ones((5, 5), np.uint8))[:h, :w]
+    ctx.set_tma(tma)
+    try:
+        for name, l, stack, ft, ht in (("synthetic", lay, synthetic_stack(lay, 60 + border), 20, 1 << 15),
+                                       ("noise", lay, noise, 45, 1 << 12), ("ragged", rag, rstack, 25, 1 << 10)):
+            for lb, bl in ((0, 5), (3, 2), (5, 1)):
+                d = api.make_desc(l, border=border, fast_threshold=ft, harris_threshold=ht, log_bucket=lb,
+                                  bucket_limit=bl, words=0)
+                kp, lv, _ = ctx.extract_pyramid(stack, d, cap=1 << 16)
+                okp, olv, _ = oracle_pyramid(oracle, stack, l, border=border, fast_threshold=ft, harris_threshold=ht,
+                                             log_bucket=lb, bucket_limit=bl, words=0, cap=1 << 16)
+                assert len(okp) > 0
+                tag = "%s border %d tma %s buckets <%d,%d>" % (name, border, tma, lb, bl)
+                assert_same(kp, okp, tag + " keypoints")
+                assert_same(lv, olv, tag + " levels")
+        # descriptors with a border below 16 are refused, not silently mis-computed
+        with pytest.raises(api.PislamError) as e:
+            ctx.extract_pyramid(noise, api.make_desc(lay, border=border, words=8), cap=1 << 16)
+        assert e.value.status == api.PISLAM_ERR_UNSUPPORTED
+    finally:
+        ctx.set_tma(True)
+
+
+def test_geometry_cache_alternating(ctx, oracle):
+    """A caller alternating geometries (two cameras, or the literal fastExtract level by level) hits the per-context
+    geometry cache: after the first round no tile table is uploaded again, and results stay bit-exact."""
+    lays = [pyramid_layout(320, 240, nlevels=3), pyramid_layout(256, 160, nlevels=2), pyramid_layout(200, 120, nlevels=2)]
+    stacks = [synthetic_stack(l, 90 + i) for i, l in enumerate(lays)]
+    want = [oracle_pyramid(oracle, s_, l, log_bucket=4, bucket_limit=3) for s_, l in zip(stacks, lays)]
+    descs = [api.make_desc(l, log_bucket=4, bucket_limit=3) for l in lays]
+    uploads = []
+    for rnd in range(4):
+        for i in range(len(lays)):
+            kp, lv, desc = ctx.extract_pyramid(stacks[i], descs[i], cap=4096)
+            assert_same(kp, want[i][0], "round %d geometry %d keypoints" % (rnd, i))
+            assert_same(desc, want[i][2], "round %d geometry %d descriptors" % (rnd, i))
+        uploads.append(ctx.geometry_uploads)
+    assert uploads[1] == uploads[0] and uploads[3] == uploads[0], uploads
+
+
+def test_literal_keypoints_outside_image_rejected(ctx):
+    """Keypoints whose 31x31 patch (or 8x8 Harris window) leaves the image are refused instead of read out of bounds."""
+    img = np.full((64, 128), 9, np.uint8)
+    for x, y in ((3, 3), (120, 60), (10, 62)):
+        with pytest.raises(api.PislamError) as e:
+            ctx.orbCompute(img, np.asarray([api.encodeFast(200, x, y)], np.uint32))
+        assert e.value.status == api.PISLAM_ERR_INVALID_ARG
+        with pytest.raises(api.PislamError) as e:
+            ctx.orbCentroids(img, np.asarray([api.encodeFast(200, x, y)], np.uint32))
+        assert e.value.status == api.PISLAM_ERR_INVALID_ARG
+    with pytest.raises(api.PislamError) as e:
+        ctx.harrisScoreSobel(img, [1], [1], 0)
+    assert e.value.status == api.PISLAM_ERR_INVALID_ARG
+    with pytest.raises(api.PislamError) as e:
+        ctx.harrisScoreSobel(img, [126], [62], 0)
+    assert e.value.status == api.PISLAM_ERR_INVALID_ARG
+    with pytest.raises(ValueError):
+        ctx.extract_pyramid(np.zeros((100, 640), np.uint8), api.make_desc(VGA), cap=64)
+
+
 def test_argument_errors(ctx):
     stack = np.zeros((VGA.rows, VGA.vstep), np.uint8)
     with pytest.raises(api.PislamError) as e:

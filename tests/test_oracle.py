@@ -190,3 +190,31 @@ def test_live_reference_random_ragged_levels(reference, oracle):
                                               reference.orb_compute(img, kps[0], words)), tag
                 ncases += 1
     assert ncases == 60
+
+
+def test_pyramid_builder_matches_its_numpy_definition(oracle):
+    """the reference ships no x1/1.2 resize (README.md:28-31), so the builder's definition is
+    this repo's own numpy code (pislam_b200/pyramid.py) -- PARITY UNPINNED BY THE REFERENCE; the C oracle is pinned
+    to that numpy code here, on every pyramid layout the tests and the bench use plus ragged ones."""
+    from pislam_b200 import pyramid
+    rng = np.random.Generator(np.random.PCG64(77))
+    for lay, kind in ((pyramid.VGA, "synthetic"), (pyramid.pyramid_layout(320, 240, nlevels=4), "noise"),
+                      (pyramid.pyramid_layout(203, 117, nlevels=6, scale=1.37), "noise"),
+                      (pyramid.pyramid_layout(64, 48, nlevels=8, scale=1.2), "noise"),
+                      (pyramid.FHD, "noise")):
+        W, H = lay.widths[0], lay.heights[0]
+        base = (pyramid.synthetic_base(W, H, 3) if kind == "synthetic"
+                else rng.integers(0, 256, size=(H, W), dtype=np.uint8))
+        want = pyramid.build_stack(base, lay)
+        got = oracle.build_pyramid(base, lay)
+        assert np.array_equal(got, want), "layout %dx%d" % (W, H)
+    # single resizes incl. upscaling and 1-pixel outputs
+    src = rng.integers(0, 256, size=(37, 53), dtype=np.uint8)
+    for w, h in ((53, 37), (44, 31), (1, 1), (2, 37), (53, 1), (80, 50), (7, 5)):
+        assert np.array_equal(oracle.resize_bilinear(src, w, h), pyramid._resize_bilinear(src, w, h)), (w, h)
+    # with the blur in front: level 0 is the Gaussian.h:48-72 blur of the base, the others are resized from it
+    lay = pyramid.pyramid_layout(160, 120, nlevels=3)
+    base = rng.integers(0, 256, size=(120, 160), dtype=np.uint8)
+    blurred = np.zeros_like(base)
+    oracle.gaussian5x5(base, blurred, 160, 120)
+    assert np.array_equal(oracle.build_pyramid(base, lay, blur=True), pyramid.build_stack(blurred, lay))
