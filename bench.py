@@ -1,19 +1,27 @@
 #!/usr/bin/env python
 """Headline benchmark: ORB front-end throughput on the VGA 8-level 1.2x stacked pyramid.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--layout vga|fhd|uhd] [--impl ours|reference]
 
 A "step" is one pass of the hot path (FAST-9 -> Harris -> NMS/buckets -> oriented rBRIEF, the caller loop of
 reference demo/demo.cpp:77-101) over a batch of F synthetic stacked pyramids per GPU.  Prints ONE JSON line
 (rank 0).  `value` is device-resident throughput in Mpix/s over level pixels; `e2e` is
 the same metric through the C-ABI call with HOST (pinned) buffers, H2D of the stacks and D2H of the records
-inside the timed region.  `roofline` is for the dominant kernel (front_tile_kernel) and `cpu_baseline` is the
-reference's own CPU implementation timed on this box's host cores on a bounded sample.
+inside the timed region; `e2e_base_frames` is the same again starting from the BASE frames (the pyramid is built on
+the GPU, SURVEY.md 8f row N1, so only 1/3 of the pixels cross PCIe).  `roofline` is for the dominant kernel
+(front_tile_kernel) and `cpu_baseline` is the reference's own CPU implementation timed on this box's host cores.
 
---impl reference runs only that CPU arm (oracle/_ref = the reference's headers compiled through the NEON shim;
-falls back to the C oracle port when that library is not present).
+`parity`: before the line is printed, the records of the timed steps (device-resident, e2e, base-frame) are compared
+with the CPU oracle for every distinct bench frame, every copy of a frame with its first copy, and -- with N > 1 --
+every rank's gathered buffer, slot by slot, with what the owning rank produced.  A mismatch prints the line with
+"parity": {"ok": false, ...} and exits with status 2.
+
+--impl reference runs only the CPU arm (oracle/_ref = the reference's own headers compiled through the NEON shim,
+run natively over the same batch on all host threads; the C oracle port when that library is absent), same
+`config`.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -29,38 +37,59 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 from pislam_b200 import pyramid as _pyr  # noqa: E402
-from pislam_b200.pyramid import synthetic_stack  # noqa: E402
-
-VGA = _pyr.VGA  # rebound by --layout (the headline metric is quoted on VGA: BASELINE.json configs[1])
 
 METRIC = "orb_frontend_vga_pyramid_throughput"
 UNIT = "Mpix/s"
-WORKLOAD = "VGA 8-level 1.2x stacked pyramid (2210x640), FAST 20 + Harris 2^15 + NMS buckets<4,3> + rBRIEF-256"
-BORDER, FAST_T, HARRIS_T, LOG_BUCKET, BUCKET_LIMIT, WORDS, CAP = 16, 20, 1 << 15, 4, 3, 8, 2048
-LAYOUTS = {"vga": ("VGA", 2048), "fhd": ("FHD", 4096), "uhd": ("UHD", 8192)}  # record capacity: SURVEY.md 8e
-N_DISTINCT = 32  # distinct synthetic frames; the batch cycles through them (each copy is its own memory)
+BORDER, FAST_T, HARRIS_T, LOG_BUCKET, BUCKET_LIMIT, WORDS = 16, 20, 1 << 15, 4, 3, 8
+# layout -> (pyramid.<name>, record capacity per frame, default frames per step per GPU)
+LAYOUTS = {"vga": ("VGA", 2048, 256), "fhd": ("FHD", 4096, 64), "uhd": ("UHD", 8192, 16)}
+LAY = _pyr.VGA  # rebound by --layout (the headline metric is quoted on VGA: BASELINE.json configs[1])
+CAP = 2048
 
 
 def n_distinct():
-    return N_DISTINCT if VGA is _pyr.VGA else 4  # large frames take seconds each to synthesise
+    return 32 if LAY is _pyr.VGA else 4  # distinct synthetic frames (large ones take seconds each); the batch cycles
+
+
+def workload():
+    name = {id(_pyr.VGA): "VGA", id(_pyr.FHD): "FHD", id(_pyr.UHD): "UHD"}[id(LAY)]
+    return "%s 8-level 1.2x stacked pyramid (%dx%d), FAST 20 + Harris 2^15 + NMS buckets<4,3> + rBRIEF-256" % (
+        name, LAY.rows, LAY.vstep)
+
+
+def config(F):
+    """Identical in both arms (the driver compares them): the workload and the batch one step processes per GPU."""
+    return {"workload": workload(), "frames_per_step_per_gpu": F, "level_pixels_per_frame": LAY.level_pixels,
+            "stack_bytes_per_frame": LAY.stack_bytes, "cap": CAP, "distinct_frames": min(F, n_distinct()),
+            "l2_policy": "inputs larger than L2 (%d MB of stacks per GPU per step)" % (F * LAY.stack_bytes >> 20)
+            if F * LAY.stack_bytes > (126 << 20) else
+            "inputs smaller than L2 (%d MB): L2 flushed between steps is NOT done, quote only the default batch"
+            % (F * LAY.stack_bytes >> 20)}
 
 
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    except Exception:
+    except Exception:  # noqa: BLE001
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def make_frames(n):
-    base = [synthetic_stack(VGA, i) for i in range(min(n, n_distinct()))]
-    return np.stack([base[i % len(base)] for i in range(n)])
+def make_bases(n):
+    nd = min(n, n_distinct())
+    return [_pyr.synthetic_base(LAY.widths[0], LAY.heights[0], 0x5EED0000 + i) for i in range(nd)]
+
+
+def frames_from_bases(bases, n):
+    stacks = [_pyr.build_stack(b, LAY) for b in bases]
+    return np.stack([stacks[i % len(stacks)] for i in range(n)])
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
 class CpuReference:
-    """The reference's CPU implementation of the path on the host cores, one whole pyramid per task."""
+    """The reference's CPU implementation of the path on the host cores, one whole pyramid per task, run natively
+    (no Python between the stages): oracle/ref_driver.cpp:ref_extract_batch over the reference's own headers when
+    oracle/_ref is built, else the C oracle's po_extract_batch."""
 
     def __init__(self):
         import oracle_lib
@@ -69,39 +98,23 @@ class CpuReference:
         if oracle_lib.have_reference():
             try:
                 self.ref = oracle_lib.Reference()
-            except OSError:
+            except (OSError, AttributeError):
                 self.ref = None
         self.kind = "reference" if self.ref is not None else "port"
 
-    def _ref_frame(self, stack):
-        """The caller loop of demo/demo.cpp:77-101.  orbCompute runs per level on level-local keypoints (same
-        descriptors as one call on stack coordinates, and valid for stacks taller than the 12-bit y range)."""
-        ref = self.ref
-        out = np.zeros_like(stack)
-        n = 0
-        for w, h, r in zip(VGA.widths, VGA.heights, VGA.row_offsets):
-            ref.fast_detect(stack, out, BORDER, w, h, FAST_T, row0=r)
-            ref.fast_score_harris(stack, out, BORDER, w, h, HARRIS_T, row0=r)
-            kp = ref.fast_extract(out, BORDER, w, h, LOG_BUCKET, BUCKET_LIMIT, row0=r, cap=CAP * 4)
-            ref.orb_compute(stack[r:], kp, WORDS)
-            n += len(kp)
-        return n
-
     def run(self, stacks, nthreads):
         """Processes every frame once on `nthreads` host threads; returns (seconds, total keypoints)."""
-        nf = stacks.shape[0]
         t0 = time.perf_counter()
-        if self.ref is None:
-            counts = self.oracle.extract_batch(stacks, VGA.widths, VGA.heights, VGA.row_offsets, nthreads,
+        if self.ref is not None:
+            counts = self.ref.extract_batch(stacks, LAY.widths, LAY.heights, LAY.row_offsets, nthreads,
+                                            fast_threshold=FAST_T, harris_threshold=HARRIS_T, log_bucket=LOG_BUCKET,
+                                            bucket_limit=BUCKET_LIMIT, cap=CAP * 4)
+        else:
+            counts = self.oracle.extract_batch(stacks, LAY.widths, LAY.heights, LAY.row_offsets, nthreads,
                                                border=BORDER, fast_threshold=FAST_T, harris_threshold=HARRIS_T,
                                                log_bucket=LOG_BUCKET, bucket_limit=BUCKET_LIMIT, words=WORDS,
                                                cap=CAP * 4)
-            total = int(counts.sum())
-        else:
-            from concurrent.futures import ThreadPoolExecutor
-            with ThreadPoolExecutor(nthreads) as ex:  # ctypes releases the GIL inside the reference calls
-                total = sum(ex.map(self._ref_frame, [stacks[f] for f in range(nf)]))
-        return time.perf_counter() - t0, total
+        return time.perf_counter() - t0, int(counts.sum())
 
 
 def cpu_cores():
@@ -111,14 +124,29 @@ def cpu_cores():
         return os.cpu_count() or 1
 
 
+def cpu_baseline(cpu, stacks, cores):
+    """All-cores and single-thread numbers on a bounded sample of the bench batch (the reference is single-threaded
+    by design, demo/demo.cpp:75,103; frame-parallel threads are the fairest use of the whole host)."""
+    cpu.run(stacks[:max(cores, 1)], cores)  # warm-up (page-in, thread start)
+    n_all = len(stacks)
+    dt, kp = cpu.run(stacks, cores)
+    n1 = max(2, min(16, n_all))
+    dt1, _ = cpu.run(stacks[:n1], 1)
+    return {"value": LAY.level_pixels * n_all / dt / 1e6, "unit": UNIT, "cores": cores, "kind": cpu.kind,
+            "keypoints_per_s": kp / dt,
+            "sample": "%d frames (one step's batch) once on %d host threads, one pyramid per task" % (n_all, cores),
+            "single_thread": {"value": LAY.level_pixels * n1 / dt1 / 1e6, "unit": UNIT, "cores": 1,
+                              "ms_per_frame": 1e3 * dt1 / n1, "sample": "%d frames on 1 thread" % n1}}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cpu = CpuReference()
     cores = cpu_cores()
-    nf = max(cores * 4, 8)  # a bounded sample of the same workload: a few frames per host thread
-    stacks = make_frames(nf)
+    F = args.frames
+    stacks = frames_from_bases(make_bases(F), F)
     for _ in range(args.warmup):
         cpu.run(stacks[:max(cores, 1)], cores)
     times, kpts = [], 0
@@ -126,16 +154,19 @@ def run_reference_arm(args):
         dt, kpts = cpu.run(stacks, cores)
         times.append(dt)
     total = sum(times)
-    mpix = VGA.level_pixels * nf * args.steps / total / 1e6
+    mpix = LAY.level_pixels * F * args.steps / total / 1e6
+    n1 = max(2, min(16, F))
+    dt1, _ = cpu.run(stacks[:n1], 1)
     line = {
         "impl": "reference", "metric": METRIC, "value": mpix, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": nf, "level_pixels_per_frame": VGA.level_pixels,
-                   "keypoints_per_frame": kpts / nf},
-        "keypoints_per_s": kpts * args.steps / total,
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config(F),
+        "keypoints_per_frame": kpts / F, "keypoints_per_s": kpts * args.steps / total,
         "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": cores, "kind": cpu.kind,
-                         "sample": "%d frames per step on %d host threads, one pyramid per task" % (nf, cores)},
+                         "sample": "%d frames per step on %d host threads, one pyramid per task, %d steps" % (
+                             F, cores, args.steps),
+                         "single_thread": {"value": LAY.level_pixels * n1 / dt1 / 1e6, "unit": UNIT, "cores": 1,
+                                           "ms_per_frame": 1e3 * dt1 / n1, "sample": "%d frames on 1 thread" % n1}},
         "e2e": {"value": mpix, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -195,6 +226,71 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+class ParityGate:
+    """Compares records with the CPU oracle (tests/oracle_lib.py -- the checker, never the thing measured)."""
+
+    def __init__(self, api, bases, F):
+        import oracle_lib
+        self.api, self.F = api, F
+        oracle = oracle_lib.Oracle()
+        self.want = []
+        for b in bases:
+            stack = oracle.build_pyramid(b, LAY)
+            self.want.append(oracle.extract_pyramid(stack, LAY.widths, LAY.heights, LAY.row_offsets, border=BORDER,
+                                                    fast_threshold=FAST_T, harris_threshold=HARRIS_T,
+                                                    log_bucket=LOG_BUCKET, bucket_limit=BUCKET_LIMIT, words=WORDS))
+        self.report = {"ok": True, "oracle_frames": len(self.want), "checks": {}}
+
+    def check_records(self, name, buf):
+        """buf: host uint8 copy of F records.  Every frame against the oracle result of its distinct source."""
+        recs = self.api.parse_records(buf, self.F, CAP, WORDS)
+        bad = 0
+        for f, (kp, lv, desc, _, n_total) in enumerate(recs):
+            okp, olv, odesc = self.want[f % len(self.want)]
+            if not (n_total == len(okp) and np.array_equal(kp, okp) and np.array_equal(lv, olv) and
+                    np.array_equal(desc, odesc)):
+                bad += 1
+        self.report["checks"][name] = {"frames": len(recs), "mismatches": bad}
+        if bad:
+            self.report["ok"] = False
+        return recs
+
+    @staticmethod
+    def live_hashes(recs):
+        """One digest per frame over the live part of its record (count, keypoints, levels, descriptors)."""
+        out = []
+        for kp, lv, desc, level_start, n_total in recs:
+            h = hashlib.blake2b(digest_size=8)
+            h.update(np.asarray([len(kp), n_total], np.uint32).tobytes())
+            h.update(level_start.tobytes())
+            h.update(kp.tobytes())
+            h.update(lv.tobytes())
+            h.update(desc.tobytes())
+            out.append(h.hexdigest())
+        return out
+
+    def check_gathered(self, name, buf, world, rank, dist):
+        """buf: host copy of this rank's gathered buffer (world x F records).  Slot r must hold exactly what rank r
+        produced: per-frame digests of the live bytes, exchanged with all_gather_object."""
+        recs = self.api.parse_records(buf, world * self.F, CAP, WORDS)
+        mine = self.live_hashes(recs[rank * self.F:(rank + 1) * self.F])
+        owners = [None] * world
+        dist.all_gather_object(owners, mine)
+        bad = 0
+        for r in range(world):
+            got = self.live_hashes(recs[r * self.F:(r + 1) * self.F])
+            bad += sum(1 for a, b in zip(got, owners[r]) if a != b)
+        # and the local slot itself against the oracle
+        for f in range(self.F):
+            okp, olv, odesc = self.want[f % len(self.want)]
+            kp, lv, desc, _, n_total = recs[rank * self.F + f]
+            if not (np.array_equal(kp, okp) and np.array_equal(desc, odesc)):
+                bad += 1
+        self.report["checks"][name] = {"slots": world * self.F, "mismatches": bad}
+        if bad:
+            self.report["ok"] = False
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -210,15 +306,20 @@ def run_gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     F = args.frames
-    desc = api.make_desc(VGA, border=BORDER, fast_threshold=FAST_T, harris_threshold=HARRIS_T,
+    desc = api.make_desc(LAY, border=BORDER, fast_threshold=FAST_T, harris_threshold=HARRIS_T,
                          log_bucket=LOG_BUCKET, bucket_limit=BUCKET_LIMIT, words=WORDS)
     lay = api.record_layout(CAP, WORDS)
     rec_bytes = lay["bytes"]
-    frame_bytes = VGA.stack_bytes
+    frame_bytes = LAY.stack_bytes
+    W, H = LAY.widths[0], LAY.heights[0]
 
-    frames = make_frames(F)  # every rank: its own F frames (weak scaling); same synthetic set per rank
-    h_stacks = torch.empty((F, VGA.rows, VGA.vstep), dtype=torch.uint8, pin_memory=True)
+    bases = make_bases(F)  # every rank: its own F frames (weak scaling); same synthetic set per rank
+    frames = frames_from_bases(bases, F)
+    h_stacks = torch.empty((F, LAY.rows, LAY.vstep), dtype=torch.uint8, pin_memory=True)
     h_stacks.numpy()[:] = frames
+    h_bases = torch.empty((F, H, W), dtype=torch.uint8, pin_memory=True)
+    for f in range(F):
+        h_bases.numpy()[f] = bases[f % len(bases)]
     h_records = torch.empty(F * rec_bytes, dtype=torch.uint8, pin_memory=True)
     d_stacks = h_stacks.to("cuda", non_blocking=False)
     # two gather buffers: the all-gather of step k runs under the kernels of step k+1
@@ -231,48 +332,45 @@ def run_gpu_arm(args):
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
     gather = "none"
     if world > 1:
-        try:
-            uid = [api.comm_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(uid, src=0)
-            ctx.comm_init(world, rank, uid[0])
-            gather = "ncclAllGather issued by libpislam_b200 on the extraction stream"
-        except Exception as e:  # noqa: BLE001
-            gather = "torch.distributed.all_gather_into_tensor (C-ABI comm unavailable: %s)" % e
+        uid = [api.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(world, rank, uid[0])
+        gather = "one all-gather of the records per step, issued by libpislam_b200 on its second stream"
+    gate = None if args.no_parity else ParityGate(api, bases, F)
 
     def step_device():
         """inputs resident in HBM; results (this rank's records, all-gathered when N>1) left in HBM"""
-        if world > 1 and gather.startswith("ncclAllGather"):
+        if world > 1:
             buf = d_alls[turn[0]]
             turn[0] ^= 1
             st = ctx.extract_allgather_ptr(d_stacks.data_ptr(), frame_bytes, F, desc, CAP, buf.data_ptr())
         else:
             st = ctx.extract_batch_ptr(d_stacks.data_ptr(), frame_bytes, F, desc, CAP, d_records.data_ptr(),
                                        asynchronous=True)
-            if world > 1:
-                with torch.cuda.stream(stream):
-                    dist.all_gather_into_tensor(d_all, d_records)
         if st != 0:
             raise RuntimeError("extract failed: %d" % st)
 
-    def step_e2e():
-        """the call a user makes: HOST stacks in, HOST records out (H2D + kernels + D2H inside); with N > 1 the
-        records are extracted into this rank's slot of the device gather buffer, all-gathered over NVLink, and the
-        rank's own records are read back to the host"""
-        if world == 1:
-            st = ctx.extract_batch_ptr(h_stacks.data_ptr(), frame_bytes, F, desc, CAP, h_records.data_ptr())
-        else:
-            st = ctx.extract_batch_ptr(h_stacks.data_ptr(), frame_bytes, F, desc, CAP, d_records.data_ptr())
-            if st in (0, api.PISLAM_ERR_CAPACITY):
-                if gather.startswith("ncclAllGather"):
-                    g = ctx.allgather_ptr(d_all.data_ptr(), F * rec_bytes)
-                    if g != 0:
-                        raise RuntimeError("allgather failed: %d" % g)
-                with torch.cuda.stream(stream):
-                    if not gather.startswith("ncclAllGather"):
-                        dist.all_gather_into_tensor(d_all, d_records)
-                    h_records.copy_(d_records, non_blocking=True)
+    def e2e_tail(st):
+        """N > 1: the records extracted into this rank's slot are all-gathered over NVLink and the rank's own records
+        are read back to the host"""
         if st not in (0, api.PISLAM_ERR_CAPACITY):
             raise RuntimeError("extract failed: %d" % st)
+        if world > 1:
+            g = ctx.allgather_ptr(d_all.data_ptr(), F * rec_bytes)
+            if g != 0:
+                raise RuntimeError("allgather failed: %d" % g)
+            with torch.cuda.stream(stream):
+                h_records.copy_(d_records, non_blocking=True)
+
+    def step_e2e():
+        """the call a user makes: HOST stacks in, HOST records out (H2D + kernels + D2H inside the call)"""
+        dst = h_records.data_ptr() if world == 1 else d_records.data_ptr()
+        e2e_tail(ctx.extract_batch_ptr(h_stacks.data_ptr(), frame_bytes, F, desc, CAP, dst))
+
+    def step_e2e_base():
+        """HOST base frames in, HOST records out: the pyramid is built on the GPU"""
+        dst = h_records.data_ptr() if world == 1 else d_records.data_ptr()
+        e2e_tail(ctx.extract_frames_ptr(h_bases.data_ptr(), W, W * H, F, desc, CAP, dst))
 
     def barrier():
         if world > 1:
@@ -300,7 +398,8 @@ def run_gpu_arm(args):
             ms = float(t.item())
         return ms, ctx.launch_count - l0, t0, t1
 
-    for _ in range(max(args.warmup, 3)):
+    W_ = max(args.warmup, 3)
+    for _ in range(W_):
         step_device()
     sampler = ClockSampler(local) if rank == 0 else None
     ms_dev, launches, t0, t1 = timed(step_device, args.steps)
@@ -320,63 +419,92 @@ def run_gpu_arm(args):
         clocks["window"] = ("timed region + %d identical untimed steps right after it (region %.1f ms < sampling "
                             "period)" % (extra_steps, (t1 - t0) * 1e3)) if extra_steps else "timed region"
 
-    # keypoints actually produced (from the records of the last step)
+    # keypoints actually produced (from the records of the last step) and the parity gate on them
     hdr = d_records.view(F, rec_bytes)[:, :8].contiguous().cpu().numpy().view(np.uint32)
     kpts_local = int(hdr[:, 0].sum())
     overflow = int((hdr[:, 1] > hdr[:, 0]).sum())
+    if gate:
+        if world > 1:
+            for i, buf in enumerate(d_alls):
+                gate.check_gathered("gathered_buffer_%d" % i, buf.cpu().numpy(), world, rank, dist)
+        else:
+            gate.check_records("device_resident", d_records.cpu().numpy())
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(W_):
         step_e2e()
     # events on the ctx stream span the H2D copies, the kernels, the D2H copies and any host-side gaps
+    h_records.zero_()
     ms_e2e, _, _, _ = timed(step_e2e, args.steps)
+    if gate:
+        gate.check_records("e2e_host_records", h_records.numpy())
+
+    for _ in range(W_):
+        step_e2e_base()
+    h_records.zero_()
+    ms_e2e_base, launches_base, _, _ = timed(step_e2e_base, args.steps)
+    if gate:
+        gate.check_records("e2e_base_frames_host_records", h_records.numpy())
 
     # roofline of the dominant kernel: per-kernel CUDA events (library profiling mode), same inputs
-    roof = None
-    latency = None
+    roof = latency = demo_ms = base_dev = None
     if rank == 0:
         roof = kernel_roofline(ctx, api, d_stacks, frame_bytes, F, desc, d_records, kpts_local, args.steps)
+        base_dev = base_frames_device(ctx, api, torch, h_bases, W, H, F, desc, d_records, args.steps, stream)
         latency = single_frame_latency(ctx, h_stacks[0].numpy(), desc)  # pinned host frame
+        if LAY is _pyr.VGA:
+            demo_ms = literal_demo_loop_ms(ctx, h_stacks[0].numpy())
 
     if world > 1:
-        t = torch.tensor([kpts_local, overflow], device="cuda", dtype=torch.int64)
+        t = torch.tensor([kpts_local, overflow, 0 if (gate is None or gate.report["ok"]) else 1], device="cuda",
+                         dtype=torch.int64)
         dist.all_reduce(t)
-        kpts_total, overflow = int(t[0].item()), int(t[1].item())
+        kpts_total, overflow, parity_bad_ranks = int(t[0].item()), int(t[1].item()), int(t[2].item())
     else:
         kpts_total = kpts_local
+        parity_bad_ranks = 0 if (gate is None or gate.report["ok"]) else 1
 
+    ok = True
     if rank == 0:
-        pix = VGA.level_pixels * F * world
+        pix = LAY.level_pixels * F * world
         value = pix * args.steps / (ms_dev * 1e-3) / 1e6
         e2e_value = pix * args.steps / (ms_e2e * 1e-3) / 1e6
-        cpu = CpuReference()
-        cores = cpu_cores()
-        nf = max(cores * 4, 8)
-        sample = make_frames(nf)
-        cpu.run(sample[:max(cores, 1)], cores)
-        dt, ck = cpu.run(sample, cores)
+        e2e_base_value = pix * args.steps / (ms_e2e_base * 1e-3) / 1e6
+        cpu_line = None
+        if not args.no_cpu:
+            cpu = CpuReference()
+            cpu_line = cpu_baseline(cpu, frames, cpu_cores())
+        parity = None
+        if gate:
+            parity = gate.report
+            parity["ranks_with_mismatches"] = parity_bad_ranks
+            parity["ok"] = parity["ok"] and parity_bad_ranks == 0
+            ok = parity["ok"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": F, "level_pixels_per_frame": VGA.level_pixels,
-                       "stack_bytes_per_frame": frame_bytes, "keypoints_per_frame": kpts_total / (F * world),
-                       "l2_policy": "inputs larger than L2 (%d MB of stacks per GPU per step)" % (F * frame_bytes >> 20),
-                       "cap": CAP, "capacity_overflows": overflow, "gather": gather,
-                       "parallelism": "frames sharded one batch per GPU, one all-gather of records per step "
-                                      "(overlapping the next step's kernels)" if world > 1 else "single GPU",
-                       "numa_node_rank0": numa},
+            "warmup": W_, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config(F),
+            "keypoints_per_frame": kpts_total / (F * world),
             "keypoints_per_s": kpts_total * args.steps / (ms_dev * 1e-3),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": F * VGA.level_pixels,
+            "details": {"capacity_overflows": overflow, "gather": gather,
+                        "parallelism": "frames sharded one batch per GPU, one all-gather of records per step "
+                                       "(overlapping the next step's kernels)" if world > 1 else "single GPU",
+                        "numa_node_rank0": numa},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": F * LAY.level_pixels,
                     "h2d_note": "level pixels only: the padding right of each level is not uploaded",
                     "d2h_bytes_per_step": F * rec_bytes, "ms_per_step": ms_e2e / args.steps,
                     "keypoints_per_s": kpts_total * args.steps / (ms_e2e * 1e-3)},
+            "e2e_base_frames": {"value": e2e_base_value, "unit": UNIT, "h2d_bytes_per_step": F * W * H,
+                                "d2h_bytes_per_step": F * rec_bytes, "ms_per_step": ms_e2e_base / args.steps,
+                                "note": "host BASE frames in, host records out: pislam_b200_extract_frames builds "
+                                        "the 8-level pyramid on the GPU; Mpix/s over the same level pixels",
+                                "gpu_launches": launches_base, "device_resident": base_dev},
             "gpu_launches": launches,
             "single_frame_latency_us": latency,
+            "literal_stage_demo_loop_ms_per_frame": demo_ms,
+            "parity": parity,
             "clocks": clocks,
             "roofline": roof,
-            "cpu_baseline": {"value": VGA.level_pixels * nf / dt / 1e6, "unit": UNIT, "cores": cores,
-                             "kind": cpu.kind, "keypoints_per_s": ck / dt,
-                             "sample": "%d frames once on %d host threads, one pyramid per task" % (nf, cores)},
+            "cpu_baseline": cpu_line,
         }
         emit(line)
     # teardown order matters: torch may still hold blocks it used on the ctx stream (an ExternalStream);
@@ -384,7 +512,7 @@ def run_gpu_arm(args):
     if world > 1:
         dist.barrier()
     barrier()
-    del d_records, d_all, d_alls, d_stacks, h_stacks, h_records, stream
+    del d_records, d_all, d_alls, d_stacks, h_stacks, h_records, h_bases, stream
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
     if world > 1:
@@ -394,6 +522,10 @@ def run_gpu_arm(args):
             pass
         dist.destroy_process_group()
     ctx.close()
+    if parity_bad_ranks:
+        sys.stderr.write("bench.py: PARITY MISMATCH against the oracle -- the numbers above are void\n")
+        sys.exit(2)
+    return ok
 
 
 def single_frame_latency(ctx, stack, desc, iters=200):
@@ -407,6 +539,67 @@ def single_frame_latency(ctx, stack, desc, iters=200):
     for _ in range(iters):
         ctx.extract_pyramid(stack, desc, cap=CAP)
     return (time.perf_counter() - t0) / iters * 1e6
+
+
+def literal_demo_loop_ms(ctx, stack, iters=5):
+    """The reference demo's own loop (demo/demo.cpp:77-101) through the literal stage calls -- what a user who only
+    swaps the include path gets: per level fastDetect -> fastScoreHarris -> fastExtract (img and out round-trip
+    through the device on every call), then one orbCompute.  examples/demo (C++, same loop against
+    include/pislam/*.h) when it has been built, else the ctypes mirror.  ms per frame, wall clock."""
+    exe = os.path.join(ROOT, "examples", "demo")
+    if os.path.exists(exe):
+        try:
+            import tempfile
+            with tempfile.NamedTemporaryFile(suffix=".raw") as f:
+                f.write(np.ascontiguousarray(stack).tobytes())
+                f.flush()
+                best = None
+                for _ in range(3):
+                    out = subprocess.run([exe, f.name], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+                                         timeout=120).stdout
+                    for ln in out.splitlines():
+                        if ln.startswith("stages:"):
+                            ms = float(ln.rsplit(",", 1)[1].split()[0])
+                            best = ms if best is None else min(best, ms)
+                if best is not None:
+                    return {"ms": best, "how": "examples/demo (C++ against include/pislam/*.h), best of 3 processes"}
+        except Exception:  # noqa: BLE001
+            pass
+    out = np.zeros_like(stack)
+
+    def once():
+        out[:] = 0
+        pts = []
+        for w, h, r in zip(LAY.widths, LAY.heights, LAY.row_offsets):
+            ctx.fastDetect(w, h, stack, out, FAST_T, border=BORDER, row0=r)
+            ctx.fastScoreHarris(w, h, stack, HARRIS_T, out, border=BORDER, row0=r)
+            kp = ctx.fastExtract(w, h, out, border=BORDER, row0=r)
+            pts.append(kp + np.uint32(r))
+        ctx.orbCompute(stack, np.concatenate(pts), words=WORDS)
+    once()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        once()
+    return {"ms": (time.perf_counter() - t0) / iters * 1e3, "how": "ctypes mirror of the literal stage calls"}
+
+
+def base_frames_device(ctx, api, torch, h_bases, W, H, F, desc, d_records, steps, stream):
+    """Device-resident base frames -> records (pyramid_build_kernel + the fused path in L2-sized chunks)."""
+    d_bases = h_bases.to("cuda")
+    for _ in range(3):
+        assert ctx.extract_frames_ptr(d_bases.data_ptr(), W, W * H, F, desc, CAP, d_records.data_ptr()) == 0
+    ctx.set_profiling(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        assert ctx.extract_frames_ptr(d_bases.data_ptr(), W, W * H, F, desc, CAP, d_records.data_ptr()) == 0
+    e1.record(stream)
+    ms, cnt = ctx.kernel_times()
+    ctx.set_profiling(False)
+    total = e0.elapsed_time(e1)
+    del d_bases
+    return {"ms_per_step": total / steps, "value": LAY.level_pixels * F * steps / (total * 1e-3) / 1e6, "unit": UNIT,
+            "pyramid_build_kernel_ms_per_step": ms[3] / steps, "note": "blocking call per step, profiling events on"}
 
 
 def kernel_roofline(ctx, api, d_stacks, frame_bytes, F, desc, d_records, kpts, steps):
@@ -424,13 +617,13 @@ def kernel_roofline(ctx, api, d_stacks, frame_bytes, F, desc, d_records, kpts, s
     if cnt[0] == 0:
         return None
     t_front = ms[0] / cnt[0] * 1e-3
-    alg_bytes = VGA.level_pixels * F + 4 * kpts
+    alg_bytes = LAY.level_pixels * F + 4 * kpts
     achieved = alg_bytes / t_front / 1e9
     traffic, traffic_src = None, None
     try:  # DRAM bytes of one launch from the committed ncu --set full capture (same workload and batch size)
         with open(os.path.join(ROOT, "profiles", "front_kernel_traffic.json")) as f:
             tr = json.load(f)
-        if tr["frames_per_launch"] == F and VGA is _pyr.VGA:
+        if tr["frames_per_launch"] == F and LAY is _pyr.VGA:
             traffic, traffic_src = tr["dram_bytes_read"] + tr["dram_bytes_write"], tr["source"]
     except Exception:  # noqa: BLE001
         pass
@@ -442,22 +635,52 @@ def kernel_roofline(ctx, api, d_stacks, frame_bytes, F, desc, d_records, kpts, s
 
 
 def bind_to_gpu_numa(local_rank):
-    """Pin this process (and so its first-touch pinned buffers) to the CPUs of the GPU's NUMA node."""
+    """Pin this process (and so its first-touch pinned buffers) to the CPUs of the GPU's NUMA node: sysfs first, the
+    CPU-affinity column of `nvidia-smi topo -m` when the container hides the node."""
+    def apply(cpus):
+        cpus = set(cpus) & os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return True
+        return False
+
+    def parse_list(s):
+        cpus = set()
+        for part in s.strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        return cpus
     try:
         import torch
         p = torch.cuda.get_device_properties(local_rank)
         bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
         node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
-        if node < 0:
-            return None
-        cpus = set()
-        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
-            a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if cpus:
-            os.sched_setaffinity(0, cpus)
+        if node >= 0 and apply(parse_list(open("/sys/devices/system/node/node%d/cpulist" % node).read())):
             return node
+    except Exception:  # noqa: BLE001
+        pass
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+                             timeout=20).stdout
+        import re
+        clean = re.sub(r"\x1b\[[0-9;]*m", "", out)
+        head = None
+        for ln in clean.splitlines():
+            cols = [c.strip() for c in ln.split("\t") if c.strip()]
+            if not cols:
+                continue
+            if head is None and any("CPU Affinity" in c for c in cols):
+                head = cols
+                continue
+            if head and cols[0] == "GPU%d" % local_rank:
+                # the header lacks the row-label column: values align with head shifted by one
+                idx = next(i for i, c in enumerate(head) if "CPU Affinity" in c) + 1
+                nidx = next((i for i, c in enumerate(head) if "NUMA Affinity" in c), None)
+                if idx < len(cols) and apply(parse_list(cols[idx])):
+                    try:
+                        return int(cols[nidx + 1]) if nidx is not None else "cpus " + cols[idx]
+                    except (ValueError, IndexError):
+                        return "cpus " + cols[idx]
     except Exception:  # noqa: BLE001
         pass
     return None
@@ -474,17 +697,19 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--frames", type=int, default=256, help="stacked pyramids per step per GPU")
+    ap.add_argument("--frames", type=int, default=0, help="stacked pyramids per step per GPU (default: 256 VGA, "
+                                                          "64 1080p, 16 4K)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layout", default="vga", choices=sorted(LAYOUTS),
                     help="pyramid geometry (default vga = the headline config; fhd/uhd = BASELINE configs 3 and 5)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (sweeps)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-bench parity gate (never for a quoted number)")
     args = ap.parse_args()
-    global VGA, CAP, WORKLOAD
-    name, CAP = LAYOUTS[args.layout]
-    VGA = getattr(_pyr, name)
-    if args.layout != "vga":
-        WORKLOAD = "%s 8-level 1.2x stacked pyramid (%dx%d), FAST 20 + Harris 2^15 + NMS buckets<4,3> + rBRIEF-256" % (
-            name, VGA.rows, VGA.vstep)
+    global LAY, CAP
+    name, CAP, default_frames = LAYOUTS[args.layout]
+    LAY = getattr(_pyr, name)
+    if args.frames <= 0:
+        args.frames = default_frames
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -230,6 +230,30 @@ class Reference(_Lib):
 
     def __init__(self):
         super().__init__(REF_SO, "ref_")
+        f = self.lib.ref_extract_batch
+        f.argtypes = [u8p, C.c_long, C.c_int, C.c_int, C.c_int, intp, intp, intp, C.c_int, C.c_int32, C.c_int,
+                      C.c_int, C.c_int, C.c_int, intp, u32p, u32p]
+        f.restype = C.c_int
+
+    def extract_batch(self, stacks, widths, heights, row_offsets, nthreads, fast_threshold=20,
+                      harris_threshold=1 << 15, log_bucket=0, bucket_limit=5, cap=1 << 14, keep=False):
+        """The reference's caller loop (demo/demo.cpp:77-101) over [nframes, rows, vstep] stacks on `nthreads`
+        std::threads, natively (oracle/ref_driver.cpp:ref_extract_batch; border 16, 8 words).  Returns counts
+        (and kp [nf][cap], desc [nf][cap*8] when keep)."""
+        nf = stacks.shape[0]
+        w = np.asarray(widths, np.int32)
+        h = np.asarray(heights, np.int32)
+        r = np.asarray(row_offsets, np.int32)
+        counts = np.zeros(nf, np.int32)
+        kp = np.zeros((nf, cap), np.uint32) if keep else None
+        desc = np.zeros((nf, cap * 8), np.uint32) if keep else None
+        st = self.lib.ref_extract_batch(_p(stacks, u8p), stacks.shape[1] * stacks.shape[2], nf, stacks.shape[2],
+                                        len(w), _p(w, intp), _p(h, intp), _p(r, intp), fast_threshold,
+                                        harris_threshold, log_bucket, bucket_limit, cap, nthreads,
+                                        _p(counts, intp), _p(kp, u32p) if keep else None,
+                                        _p(desc, u32p) if keep else None)
+        assert st == 0, "ref_extract_batch: %d" % st
+        return (counts, kp, desc) if keep else counts
 
 
 def have_reference():

@@ -218,3 +218,22 @@ def test_pyramid_builder_matches_its_numpy_definition(oracle):
     blurred = np.zeros_like(base)
     oracle.gaussian5x5(base, blurred, 160, 120)
     assert np.array_equal(oracle.build_pyramid(base, lay, blur=True), pyramid.build_stack(blurred, lay))
+
+
+def test_reference_batch_driver_equals_the_oracle(oracle, reference):
+    """oracle/ref_driver.cpp:ref_extract_batch (the reference's caller loop run natively over a batch, bench.py's
+    CPU arm) returns, frame by frame, what the oracle's po_extract_pyramid returns."""
+    from pislam_b200 import pyramid
+    stacks = np.stack([pyramid.synthetic_stack(pyramid.VGA, 700 + i) for i in range(5)])
+    lay = pyramid.VGA
+    for lb, bl in ((4, 3), (0, 5)):
+        for nthreads in (1, 3):
+            counts, kp, desc = reference.extract_batch(stacks, lay.widths, lay.heights, lay.row_offsets, nthreads,
+                                                       log_bucket=lb, bucket_limit=bl, cap=4096, keep=True)
+            for f in range(len(stacks)):
+                okp, _, odesc = oracle.extract_pyramid(stacks[f], lay.widths, lay.heights, lay.row_offsets,
+                                                       log_bucket=lb, bucket_limit=bl)
+                n = int(counts[f])
+                assert n == len(okp)
+                assert np.array_equal(kp[f, :n], okp)
+                assert np.array_equal(desc[f, :n * 8].reshape(n, 8), odesc)
