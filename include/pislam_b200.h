@@ -56,6 +56,9 @@ long pislam_b200_geometry_uploads(pislam_ctx* ctx);
 /* Tile staging of the fused kernel: 1 = TMA box loads (default), 0 = plain loads.  The TMA path is also
  * skipped automatically when vstep / frame_stride / the base address are not multiples of 16 bytes. */
 int pislam_b200_set_tma(pislam_ctx* ctx, int enable);
+/* Sub-batching of the fused calls: frames per sub-batch (0 = off).  The descriptor kernel of sub-batch k then runs
+ * on a second stream under the detector of sub-batch k+1, while the sub-batch's stacks are still in the L2. */
+int pislam_b200_set_sub_batch(pislam_ctx* ctx, int frames);
 /* Per-kernel timing of the fused path (bench.py's roofline): while enabled, CUDA events are recorded on
  * the ctx stream around every launch of [0] front_tile_kernel, [1] order_kernel, [2] orb_kernel,
  * [3] pyramid_build_kernel.

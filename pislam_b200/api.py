@@ -53,6 +53,7 @@ _SIGNATURES = {
     "pislam_b200_launch_count": (C.c_long, [C.c_void_p]),
     "pislam_b200_geometry_uploads": (C.c_long, [C.c_void_p]),
     "pislam_b200_set_tma": (C.c_int, [C.c_void_p, C.c_int]),
+    "pislam_b200_set_sub_batch": (C.c_int, [C.c_void_p, C.c_int]),
     "pislam_b200_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "pislam_b200_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_long)]),
     "pislam_b200_build_pyramid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_int,
@@ -114,6 +115,8 @@ def load_library(rebuild_if_stale=True):
         path = _build.build_library()
     lib = C.CDLL(path)
     for name, (res, args) in _SIGNATURES.items():
+        if override and not hasattr(lib, name):
+            continue  # an A/B build of an older revision (tools/gpu_front_ab.py) may lack the newest entry points
         f = getattr(lib, name)  # AttributeError here == a declared symbol is missing
         f.restype = res
         f.argtypes = args
@@ -231,6 +234,9 @@ class Context:
         cnt = (C.c_long * 4)()
         self._ok(self.lib.pislam_b200_kernel_times(self._h, ms, cnt))
         return list(ms), list(cnt)
+
+    def set_sub_batch(self, frames):
+        self._ok(self.lib.pislam_b200_set_sub_batch(self._h, int(frames)))
 
     def set_tma(self, enable):
         self._ok(self.lib.pislam_b200_set_tma(self._h, int(bool(enable))))

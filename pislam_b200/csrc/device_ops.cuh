@@ -42,6 +42,39 @@ __device__ __forceinline__ bool fast9_at(Ptr c, int pitch, int t) {
   return arc9(mb & 0xffffu) || arc9(md & 0xffffu);
 }
 
+// The same test with both polarities packed into one word per ring pixel (the tile kernel's phase B):
+// u = 65536*(c+t-p) + (p+t-c) = p*0xFFFF0001 + K has the "brighter" sign in bit 31 and the "darker" sign in bit 15
+// (the borrow of a negative low half can only turn c+t-p = 0 into -1 when p < c-t, impossible with t >= 0), so one
+// IMAD replaces two subtractions and one shift + one logic op collect both ring masks: bright in the high half,
+// dark in the low half, ring order reversed (irrelevant for a circular run).  The 9-run test then folds both
+// halves at once with rotations inside the 16-bit halves.
+__device__ __forceinline__ uint32_t rotl16x2(uint32_t x, int k) {  // rotate both halves left by k (1..15)
+  const uint32_t hm = (0xffffu << k) & 0xffffu;
+  const uint32_t hm2 = hm | (hm << 16);
+  return ((x << k) & hm2) | ((x >> (16 - k)) & ~hm2);
+}
+template <typename Ptr>
+__device__ __forceinline__ bool fast9_packed_at(Ptr c, int pitch, int t) {
+  const uint32_t v = c[0];
+  const uint32_t K = ((v + (uint32_t)t) << 16) + ((uint32_t)t - v);
+  uint32_t m = 0;
+#define PB_RING(dx, dy)                                               \
+  {                                                                   \
+    const uint32_t u = (uint32_t)c[(dy) * pitch + (dx)] * 0xffff0001u + K; \
+    m = (m >> 1) | (u & 0x80008000u);                                 \
+  }
+  PB_RING(-1, -3) PB_RING(0, -3) PB_RING(1, -3) PB_RING(2, -2)
+  PB_RING(3, -1) PB_RING(3, 0) PB_RING(3, 1) PB_RING(2, 2)
+  PB_RING(1, 3) PB_RING(0, 3) PB_RING(-1, 3) PB_RING(-2, 2)
+  PB_RING(-3, 1) PB_RING(-3, 0) PB_RING(-3, -1) PB_RING(-2, -2)
+#undef PB_RING
+  uint32_t r = m & rotl16x2(m, 1);   // runs of 2
+  r &= rotl16x2(r, 2);               // runs of 4
+  r &= rotl16x2(r, 4);               // runs of 8
+  r &= __byte_perm(m, 0u, 0x2301);   // ... preceded by a ninth (rotation by 8 = byte swap inside each half)
+  return r != 0u;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Harris code (reference Harris.h:37-69, 80-248).  P(r,j) = pixel (x-3+j, y-3+r), r,j = 0..7.
 // Central differences with floor halving, [1 2 1]/4 smoothing by two floor-halving adds, 6x6

@@ -87,11 +87,13 @@ struct FrontParams {
   int border, fast_t;
   int32_t harris_t;
   int log_bucket, bucket_limit;
-  int cap;      // staging / record capacity per frame
+  int cap;      // record capacity per frame; also the size of the staging overflow region
   int npieces;  // per frame
+  int tile_slot;   // staging entries every tile owns (a tile with more survivors reserves in the overflow region)
+  int stage_cap;   // staging entries per frame = ntiles * tile_slot + cap
   const TileDesc* tiles;
-  uint32_t* stage;        // [nframes][cap]
-  uint32_t* stage_count;  // [nframes]
+  uint32_t* stage;        // [nframes][stage_cap]
+  uint32_t* stage_count;  // [nframes] entries used in the overflow region
   uint32_t* piece_cnt;    // [nframes][npieces]
   uint32_t* piece_off;    // [nframes][npieces]
 };
@@ -231,11 +233,13 @@ __device__ __forceinline__ void push_if_bit(uint32_t& addr, uint32_t bits, uint3
 
 // Non-max rule of Fast.h:264-310 in position-independent form: a pixel survives iff it is >= the four
 // neighbours that precede it in raster order and > the four that follow (SURVEY.md spec F3).
+// Branch-free: the nine loads are independent (a chain of early exits costs a shared-memory round trip per test).
 __device__ __forceinline__ bool nms_survives(const uint8_t* q, int pitch) {
   const int s = q[0];
-  if (s == 0) return false;
-  return s >= q[-pitch - 1] && s >= q[-pitch] && s >= q[-pitch + 1] && s >= q[-1] && s > q[1] &&
-         s > q[pitch - 1] && s > q[pitch] && s > q[pitch + 1];
+  const int a0 = q[-pitch - 1], a1 = q[-pitch], a2 = q[-pitch + 1], a3 = q[-1];
+  const int b0 = q[1], b1 = q[pitch - 1], b2 = q[pitch], b3 = q[pitch + 1];
+  const int before = max(max(a0, a1), max(a2, a3)), after = max(max(b0, b1), max(b2, b3));
+  return (s != 0) & (s >= before) & (s > after);
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -247,18 +251,23 @@ __device__ __forceinline__ bool nms_survives(const uint8_t* q, int pitch) {
 static_assert(A_ROWS == 5, "pretest_rows and the 5-bit row mask are written for 5 rows per task");
 
 // Slow path of a corner that did not fit into list B: score it in place (rarely executed, kept out of line)
-__device__ __noinline__ void score_corner_inline(const uint8_t* s_pix, uint8_t* s_score, int idx, int dxo,
+// List entries are "rc" codes: (score-tile row << 8) | score-tile column (rows <= 65, columns <= 135), so that
+// neither the pixel address nor the score index needs a division.
+__device__ __forceinline__ int rc_row(uint32_t rc) { return (int)(rc >> 8) & 0x7f; }
+__device__ __forceinline__ int rc_col(uint32_t rc) { return (int)(rc & 0xffu); }
+
+__device__ __noinline__ void score_corner_inline(const uint8_t* s_pix, uint8_t* s_score, uint32_t rc, int dxo,
                                                  bool scored, int32_t harris_t) {
-  const int ry = idx / SC_W, sx = idx - ry * SC_W;
+  const int ry = rc_row(rc), sx = rc_col(rc);
   const uint32_t code = scored ? harris_code_at(s_pix + (ry + 3) * PIX_W + dxo + 4 + sx, PIX_W, harris_t) : 0xffu;
-  if (code) s_score[idx] = (uint8_t)code;
+  if (code) s_score[ry * SC_W + sx] = (uint8_t)code;
 }
 // Slow path of a candidate that did not fit into list A: exact FAST-9 and score in place
-__device__ __noinline__ void test_candidate_inline(const uint8_t* s_pix, uint8_t* s_score, int idx, int dxo, int t,
+__device__ __noinline__ void test_candidate_inline(const uint8_t* s_pix, uint8_t* s_score, uint32_t rc, int dxo, int t,
                                                    bool scored, int32_t harris_t) {
-  const int ry = idx / SC_W, sx = idx - ry * SC_W;
+  const int ry = rc_row(rc), sx = rc_col(rc);
   if (fast9_at(s_pix + (ry + 3) * PIX_W + dxo + 4 + sx, PIX_W, t))
-    score_corner_inline(s_pix, s_score, idx, dxo, scored, harris_t);
+    score_corner_inline(s_pix, s_score, rc, dxo, scored, harris_t);
 }
 
 #ifndef PB_TASK_LIST
@@ -359,7 +368,7 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
       }
       const uint32_t pos = warp_reserve(cand, &s_nC);
       if (cand) {
-        if (pos < CAP_A) s_listA[pos] = (uint16_t)i;
+        if (pos < CAP_A) s_listA[pos] = (uint16_t)(((i / SC_W) << 8) | (i % SC_W));
         else s_dense = 1u;
       }
     }
@@ -410,7 +419,7 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
       const uint32_t nz = __ballot_sync(0xffffffffu, acc != 0u);
       if (nz == 0u) continue;
       const uint32_t tpos = warp_atom_shared_add(nT_s, (uint32_t)__popc(nz)) + __popc(nz & ((1u << lane) - 1u));
-      if (acc) s_task[tpos] = make_uint2(acc, (uint32_t)(r0 * SC_W + 4 * wx));
+      if (acc) s_task[tpos] = make_uint2(acc, (uint32_t)((r0 << 8) | (4 * wx)));
     }
     __syncthreads();
 
@@ -424,7 +433,7 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
       const int idx0 = (int)te.y;
 #else
       if (__ballot_sync(0xffffffffu, acc != 0u) == 0u) continue;  // a warp without candidates (30 %) skips the rest
-      const int idx0 = r0 * SC_W + 4 * wx;
+      const int idx0 = (r0 << 8) | (4 * wx);
 #endif
       // one list reservation per warp for all rows
       constexpr uint32_t amask = 0xffffffffu;
@@ -444,16 +453,16 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
 #pragma unroll
         for (int i = 0; i < A_ROWS; ++i)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) push_if_bit(a, acc, 1u << (8 * k + i), (uint16_t)(idx0 + i * SC_W + k));
+          for (int k = 0; k < 4; ++k) push_if_bit(a, acc, 1u << (8 * k + i), (uint16_t)(idx0 + i * 256 + k));
       } else {  // list A is (nearly) full, adversarial tile: what does not fit is decided and scored right here
         while (acc) {
           const int b = __ffs(acc) - 1;
           acc &= acc - 1;
-          const int idx = idx0 + (b & 7) * SC_W + (b >> 3);
+          const uint32_t rc = (uint32_t)(idx0 + ((b & 7) << 8) + (b >> 3));
           if (pos < CAP_A) {
-            s_listA[pos] = (uint16_t)idx;
+            s_listA[pos] = (uint16_t)rc;
           } else {
-            test_candidate_inline(s_pix, s_score, idx, dxo, t, (x0 - 4 + idx % SC_W) < xs_end, P.harris_t);
+            test_candidate_inline(s_pix, s_score, rc, dxo, t, (x0 - 4 + rc_col(rc)) < xs_end, P.harris_t);
             s_dense = 1u;
           }
           ++pos;
@@ -466,17 +475,17 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
     const int nA = min((int)s_nA, CAP_A);
     for (int base = 0; base < nA; base += NT) {
       const int i = base + tid;
-      const int idx = i < nA ? s_listA[i] : 0;
-      const int ry = idx / SC_W, sx = idx - ry * SC_W;
-      const bool corner = i < nA && fast9_at(s_pix + (ry + 3) * PIX_W + dxo + 4 + sx, PIX_W, t);
+      const uint32_t rc = i < nA ? s_listA[i] : 0u;
+      const int ry = rc_row(rc), sx = rc_col(rc);
+      const bool corner = i < nA && fast9_packed_at(s_pix + (ry + 3) * PIX_W + dxo + 4 + sx, PIX_W, t);
       // columns >= w-border are never scored (Fast.h:172): they keep the raw 0xff flag
       const bool scored = (x0 - 4 + sx) < xs_end;
       const uint32_t pos = warp_reserve(corner, &s_nB);
       if (corner) {
         if (pos < CAP_B) {
-          s_listB[pos] = (uint16_t)(idx | (scored ? 0 : 0x8000));
+          s_listB[pos] = (uint16_t)(rc | (scored ? 0u : 0x8000u));
         } else {  // list B is full: score in place
-          score_corner_inline(s_pix, s_score, idx, dxo, scored, P.harris_t);
+          score_corner_inline(s_pix, s_score, rc, dxo, scored, P.harris_t);
           s_dense = 1u;
         }
       }
@@ -488,19 +497,19 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
     for (int base = 0; base < nB; base += NT) {
       const int i = base + tid;
       const uint32_t e = i < nB ? s_listB[i] : 0u;
-      const int idx = (int)(e & 0x7fffu);
-      const int ry = idx / SC_W, sx = idx - ry * SC_W;
+      const uint32_t rc = e & 0x7fffu;
+      const int ry = rc_row(rc), sx = rc_col(rc);
       uint32_t code = 0;
       if (i < nB) {
         code = (e & 0x8000u) ? 0xffu
                              : harris_code_at(s_pix + (ry + 3) * PIX_W + dxo + 4 + sx, PIX_W, P.harris_t);
-        if (code) s_score[idx] = (uint8_t)code;
+        if (code) s_score[ry * SC_W + sx] = (uint8_t)code;
       }
       // non-max candidates: non-zero scores on the tile's own cells
       const int cxp = sx - 4, cyp = ry - 1;
       const bool cand = code != 0 && cxp >= 0 && cxp < TW && cyp >= 0 && cyp < TH && x0 + (cxp & ~1) < xs_end &&
                         y0 + (cyp & ~1) < ys_end;
-      warp_push(cand, (uint16_t)idx, s_listA, &s_nC);
+      warp_push(cand, (uint16_t)rc, s_listA, &s_nC);
     }
     // The reference's fastDetect writes whole 16-pixel blocks with linear addressing: when the last block of row
     // y-1 runs past the pitch, its flag for "column vstep + c" is stored at out[y][c] -- and is in fact the FAST
@@ -520,8 +529,8 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
   // slot = position in the reference's output order inside the tile: row-major 2x2 cells (plain) or
   // band / bucket / position-in-bucket (bucketed; re-ranked by encoded value in phase D2)
   // records a surviving pixel (score-tile index idx) in its slot; returns the slot
-  auto emit = [&](int idx) -> int {
-    const int ry = idx / SC_W, sx = idx - ry * SC_W;
+  auto emit = [&](int ry, int sx) -> int {
+    const int idx = ry * SC_W + sx;
     const int cx = (sx - 4) >> 1, cy = (ry - 1) >> 1;
     int slot = cy * CELLS_X + cx;
     if (lb > 0) {
@@ -549,9 +558,10 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
     const int nC = (int)s_nC;
     for (int base = 0; base < nC; base += tail_nt) {
       const int i = base + tid;
-      const int idx = i < nC ? s_listA[i] : 0;
-      const bool surv = i < nC && nms_survives(s_score + idx, SC_W);
-      const int slot = surv ? emit(idx) : 0;
+      const uint32_t rc = i < nC ? s_listA[i] : (uint32_t)((1 << 8) | 4);  // idle lanes probe a harmless interior cell
+      const int ry = rc_row(rc), sx = rc_col(rc);
+      const bool surv = i < nC && nms_survives(s_score + ry * SC_W + sx, SC_W);
+      const int slot = surv ? emit(ry, sx) : 0;
       if (lb > 0) {
         const uint32_t pos = warp_reserve(surv, &s_nS);
         if (surv) s_listB[pos] = (uint16_t)slot;  // at most one survivor per cell: pos < CAP_B
@@ -571,7 +581,7 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
         else if (nms_survives(s_score + i0 + SC_W + 1, SC_W)) idx = i0 + SC_W + 1;
       }
       const bool surv = idx >= 0;
-      const int slot = surv ? emit(idx) : 0;
+      const int slot = surv ? emit(idx / SC_W, idx % SC_W) : 0;
       if (lb > 0) {
         const uint32_t pos = warp_reserve(surv, &s_nS);
         if (surv) s_listB[pos] = (uint16_t)slot;
@@ -630,21 +640,26 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
       if (lane >= d) incl += o;
     }
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    uint32_t base = 0;
-    if (lane == 31 && total) base = atomicAdd(P.stage_count + frame, total);
-    base = __shfl_sync(0xffffffffu, base, 31);
+    // every tile owns tile_slot staging entries, so the usual tile needs no reservation at all (a global atomic with a
+    // return value is a ~1 us round trip at the very end of the CTA's life); a fuller tile reserves in the overflow region
+    uint32_t base = blockIdx.x * (uint32_t)P.tile_slot;
+    if (total > (uint32_t)P.tile_slot) {
+      if (lane == 31) base = gridDim.x * (uint32_t)P.tile_slot + atomicAdd(P.stage_count + frame, total);
+      base = __shfl_sync(0xffffffffu, base, 31);
+    }
     const uint32_t excl = incl - pc;
-    uint32_t* stage = P.stage + (size_t)frame * P.cap;
+    uint32_t* stage = P.stage + (size_t)frame * P.stage_cap;
     uint32_t pos = base + excl;
 #pragma unroll
     for (int k = 0; k < WPL; ++k)
       for (uint32_t bits = w[k]; bits; bits &= bits - 1u) {
-        if (pos < (uint32_t)P.cap) stage[pos] = cells[(tid * WPL + k) * 32 + (__ffs(bits) - 1)];
+        if (pos < (uint32_t)P.stage_cap) stage[pos] = cells[(tid * WPL + k) * 32 + (__ffs(bits) - 1)];
         ++pos;
       }
     // a segment is one cell row (64 slots = 2 bitmap words) or one bucket band (64 << cb_log slots): always whole lanes
-    const int seg_lanes = (2 << cb_log) / WPL;
-    const int nseg = 32 / seg_lanes;
+    const int seg_shift = 1 + cb_log - (WPL == 2 ? 1 : 0);  // log2 of the lanes per segment
+    const int seg_lanes = 1 << seg_shift;
+    const int nseg = 32 >> seg_shift;
     const uint32_t a = __shfl_sync(0xffffffffu, excl, (tid * seg_lanes) & 31);
     const uint32_t bnext = __shfl_sync(0xffffffffu, excl, ((tid + 1) * seg_lanes) & 31);
     const uint32_t b = (tid + 1) * seg_lanes >= 32 ? total : bnext;
@@ -675,6 +690,8 @@ struct RecordLayout {
 
 struct OrderParams {
   int nlevels, npieces, cap;
+  int stage_cap;   // staging entries per frame
+  int over_cap;    // size of the staging overflow region (= cap)
   int piece_base[MAX_LEVELS + 1];
   const uint32_t* stage;
   uint32_t* stage_count;
@@ -692,7 +709,7 @@ __global__ void __launch_bounds__(ORDER_NT) order_kernel(const __grid_constant__
   const int tid = threadIdx.x, frame = blockIdx.x;
   const uint32_t* pcnt = P.piece_cnt + (size_t)frame * P.npieces;
   const uint32_t* poff = P.piece_off + (size_t)frame * P.npieces;
-  const uint32_t* stage = P.stage + (size_t)frame * P.cap;
+  const uint32_t* stage = P.stage + (size_t)frame * P.stage_cap;
   uint8_t* rec = P.records + (size_t)frame * P.rec.bytes;
   uint32_t* header = reinterpret_cast<uint32_t*>(rec);
   uint32_t* kp = reinterpret_cast<uint32_t*>(rec + P.rec.kp_off);
@@ -724,7 +741,7 @@ __global__ void __launch_bounds__(ORDER_NT) order_kernel(const __grid_constant__
       const uint32_t off = poff[p];
       for (uint32_t j = 0; j < c; ++j) {
         const uint32_t d = excl + j;
-        if (d < cap && off + j < cap) {
+        if (d < cap && off + j < (uint32_t)P.stage_cap) {
           kp[d] = stage[off + j];
           lvl[d] = (uint8_t)level;
         }
@@ -737,8 +754,9 @@ __global__ void __launch_bounds__(ORDER_NT) order_kernel(const __grid_constant__
   if (tid == 0) {
     const uint32_t total = s_running;
     const uint32_t staged = P.stage_count[frame];
-    // staging overflow loses entries: report it as "found more than stored"
-    const uint32_t n = (staged > cap) ? 0u : min(total, cap);
+    // an overflowing overflow region loses entries (its tiles alone hold more than cap keypoints): report it as
+    // "found more than stored"
+    const uint32_t n = (staged > (uint32_t)P.over_cap) ? 0u : min(total, cap);
     header[0] = n;
     header[1] = max(total, staged);
     for (int l = 0; l <= P.nlevels; ++l)

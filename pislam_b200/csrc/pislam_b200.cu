@@ -126,6 +126,8 @@ void build_brief_table(int8_t* t /* [30][256][4] */) {
   }
 }
 
+constexpr int kTileSlot = 32;  // staging entries every tile owns (FrontParams::tile_slot)
+
 struct Geometry {
   pislam_pyramid_desc d;
   int cap = 0;
@@ -187,6 +189,11 @@ struct pislam_ctx {
   int nranks = 1, rank = 0;
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_extract = nullptr;
+  // sub-batches: the descriptor kernel of sub-batch k runs on its own (high-priority) stream under the detector of
+  // sub-batch k+1, while the sub-batch's stacks are still in L2
+  cudaStream_t orb_stream = nullptr;
+  cudaEvent_t ev_sub = nullptr, ev_orb = nullptr;
+  int sub_frames = 0;  // frames per sub-batch (0: the whole call in one piece)
   struct GatherSlot {
     void* ptr = nullptr;  // gather buffer last used with this event
     cudaEvent_t done = nullptr;
@@ -219,17 +226,17 @@ int check_launch(pislam_ctx* c) {
 }
 
 // RAII-less span helpers: no-ops unless profiling is on
-void span_begin(pislam_ctx* c, int which) {
+void span_begin(pislam_ctx* c, int which, cudaStream_t st = nullptr) {
   if (!c->profiling) return;
   pislam_ctx::ProfSpan s;
   s.which = which;
   if (cudaEventCreate(&s.a) != cudaSuccess || cudaEventCreate(&s.b) != cudaSuccess) return;
-  cudaEventRecord(s.a, c->stream);
+  cudaEventRecord(s.a, st ? st : c->stream);
   c->spans.push_back(s);
 }
-void span_end(pislam_ctx* c) {
+void span_end(pislam_ctx* c, cudaStream_t st = nullptr) {
   if (!c->profiling || c->spans.empty()) return;
-  cudaEventRecord(c->spans.back().b, c->stream);
+  cudaEventRecord(c->spans.back().b, st ? st : c->stream);
 }
 
 int set_device(pislam_ctx* c) {
@@ -383,6 +390,8 @@ void fill_front_params(const pislam_ctx* c, FrontParams& P, const uint8_t* src, 
   P.bucket_limit = g.d.bucket_limit;
   P.cap = g.cap;
   P.npieces = g.npieces;
+  P.tile_slot = kTileSlot;
+  P.stage_cap = g.ntiles * kTileSlot + g.cap;
   P.tiles = g.tiles.as<TileDesc>();
   P.stage = c->stage.as<uint32_t>();
   P.stage_count = c->stage_count.as<uint32_t>();
@@ -392,7 +401,7 @@ void fill_front_params(const pislam_ctx* c, FrontParams& P, const uint8_t* src, 
 
 int reserve_front_scratch(pislam_ctx* c, int nframes) {
   const Geometry& g = *c->geo;
-  CK(c->stage.reserve((size_t)nframes * g.cap * 4, false, c->stream));
+  CK(c->stage.reserve((size_t)nframes * ((size_t)g.ntiles * kTileSlot + g.cap) * 4, false, c->stream));
   CK(c->stage_count.reserve((size_t)nframes * 4, true, c->stream));
   CK(c->piece_cnt.reserve((size_t)nframes * std::max(1, g.npieces) * 4, false, c->stream));
   CK(c->piece_off.reserve((size_t)nframes * std::max(1, g.npieces) * 4, false, c->stream));
@@ -406,6 +415,8 @@ int launch_order(pislam_ctx* c, int nframes, int words, uint8_t* d_records) {
   O.nlevels = g.d.nlevels;
   O.npieces = g.npieces;
   O.cap = g.cap;
+  O.stage_cap = g.ntiles * kTileSlot + g.cap;
+  O.over_cap = g.cap;
   for (int l = 0; l <= g.d.nlevels; ++l) O.piece_base[l] = g.piece_base[l];
   O.stage = c->stage.as<uint32_t>();
   O.stage_count = c->stage_count.as<uint32_t>();
@@ -420,8 +431,8 @@ int launch_order(pislam_ctx* c, int nframes, int words, uint8_t* d_records) {
 }
 
 // all device pointers; enqueue only
-int enqueue_extract(pislam_ctx* c, const uint8_t* d_stacks, size_t frame_stride, int nframes,
-                    const pislam_pyramid_desc* d, int cap, uint8_t* d_records) {
+int enqueue_extract_one(pislam_ctx* c, const uint8_t* d_stacks, size_t frame_stride, int nframes,
+                        const pislam_pyramid_desc* d, int cap, uint8_t* d_records, cudaStream_t orb_st) {
   if (nframes < 0 || nframes > 65535) return PISLAM_ERR_INVALID_ARG;
   CKS(validate_desc(d, cap, true));
   if (nframes == 0) return PISLAM_OK;  // an empty shard: nothing to launch
@@ -477,7 +488,11 @@ int enqueue_extract(pislam_ctx* c, const uint8_t* d_stacks, size_t frame_stride,
     // inside its level row (no wrap into the next row, which a box load would zero-fill instead)
     const bool orb_tma = tma_ok && d->vstep >= OT_W &&
                          make_tensor_map(c, &omap, d_stacks, d->vstep, g.rows, nframes, frame_stride, OT_W, OT_H) == PISLAM_OK;
-    span_begin(c, 2);
+    if (orb_st != c->stream) {  // the keypoints of this sub-batch are final once order_kernel has run
+      CK(cudaEventRecord(c->ev_sub, c->stream));
+      CK(cudaStreamWaitEvent(orb_st, c->ev_sub, 0));
+    }
+    span_begin(c, 2, orb_st);
     if (orb_tma) {
       // every CTA of the grid is resident (the kernel splits the keypoints evenly over gridDim.x CTAs)
       if (c->orb_tma_ctas_per_sm == 0) {
@@ -493,16 +508,36 @@ int enqueue_extract(pislam_ctx* c, const uint8_t* d_stacks, size_t frame_stride,
         R.records = d_records + (size_t)f0 * Q.rec.bytes;
         const long long slots = ((long long)R.nframes * cap + ORB_WARPS - 1) / ORB_WARPS;
         const dim3 grid((unsigned)std::min<long long>(slots, (long long)c->num_sms * c->orb_tma_ctas_per_sm));
-        orb_tma_kernel<<<grid, ORB_WARPS * 32, 0, c->stream>>>(R, omap);
+        orb_tma_kernel<<<grid, ORB_WARPS * 32, 0, orb_st>>>(R, omap);
         if (f0 + ORB_MAX_FRAMES < nframes) ++c->launches;
       }
     } else {
       const dim3 grid((unsigned)std::min<long long>(want, (long long)c->num_sms * 8));
-      orb_kernel<1><<<grid, ORB_WARPS * 32, 0, c->stream>>>(Q);
+      orb_kernel<1><<<grid, ORB_WARPS * 32, 0, orb_st>>>(Q);
     }
-    span_end(c);
+    span_end(c, orb_st);
     CKS(check_launch(c));
   }
+  return PISLAM_OK;
+}
+
+// all device pointers; enqueue only.  With sub_frames > 0 the call is cut into sub-batches: detector + ordering of
+// sub-batch k+1 on the ctx stream, the descriptor kernel of sub-batch k on orb_stream (it reads the sub-batch's
+// stacks while they are still in L2 and fills the detector's idle issue slots); the ctx stream is re-joined at the end.
+int enqueue_extract(pislam_ctx* c, const uint8_t* d_stacks, size_t frame_stride, int nframes,
+                    const pislam_pyramid_desc* d, int cap, uint8_t* d_records) {
+  const int sub = c->sub_frames;
+  if (sub <= 0 || nframes <= sub || !d || d->words <= 0)
+    return enqueue_extract_one(c, d_stacks, frame_stride, nframes, d, cap, d_records, c->stream);
+  const size_t rec_bytes = RecordLayout::make(cap, d->words).bytes;
+  // earlier work on the ctx stream (e.g. a consumer of the records) precedes the descriptor kernels too
+  for (int f0 = 0; f0 < nframes; f0 += sub) {
+    const int nf = std::min(sub, nframes - f0);
+    CKS(enqueue_extract_one(c, d_stacks + (size_t)f0 * frame_stride, frame_stride, nf, d, cap,
+                            d_records + (size_t)f0 * rec_bytes, c->orb_stream));
+  }
+  CK(cudaEventRecord(c->ev_orb, c->orb_stream));
+  CK(cudaStreamWaitEvent(c->stream, c->ev_orb, 0));
   return PISLAM_OK;
 }
 
@@ -697,6 +732,14 @@ int pislam_b200_create(pislam_ctx** out, int device, size_t max_stack_bytes, int
       if ((e = cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) { st = -(int)e; break; }
     }
     if ((e = cudaEventCreateWithFlags(&c->ev_extract, cudaEventDisableTiming)) != cudaSuccess) { st = -(int)e; break; }
+    {
+      int prio_lo = 0, prio_hi = 0;
+      if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) prio_hi = 0;
+      if ((e = cudaStreamCreateWithPriority(&c->orb_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) { st = -(int)e; break; }
+    }
+    if ((e = cudaEventCreateWithFlags(&c->ev_sub, cudaEventDisableTiming)) != cudaSuccess) { st = -(int)e; break; }
+    if ((e = cudaEventCreateWithFlags(&c->ev_orb, cudaEventDisableTiming)) != cudaSuccess) { st = -(int)e; break; }
+    if (const char* sf = getenv("PISLAM_B200_SUB_FRAMES")) c->sub_frames = std::max(0, atoi(sf));
     for (int i = 0; i < 2 && st == PISLAM_OK; ++i)
       if ((e = cudaEventCreateWithFlags(&c->gathers[i].done, cudaEventDisableTiming)) != cudaSuccess) st = -(int)e;
     if (st != PISLAM_OK) break;
@@ -776,6 +819,12 @@ int pislam_b200_destroy(pislam_ctx* c) {
     if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
   }
   if (c->ev_extract) cudaEventDestroy(c->ev_extract);
+  if (c->ev_sub) cudaEventDestroy(c->ev_sub);
+  if (c->ev_orb) cudaEventDestroy(c->ev_orb);
+  if (c->orb_stream) {
+    cudaStreamSynchronize(c->orb_stream);
+    cudaStreamDestroy(c->orb_stream);
+  }
   for (int i = 0; i < 2; ++i)
     if (c->gathers[i].done) cudaEventDestroy(c->gathers[i].done);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
@@ -815,6 +864,12 @@ long pislam_b200_geometry_uploads(pislam_ctx* c) { return c ? c->geo_uploads : 0
 int pislam_b200_set_tma(pislam_ctx* c, int enable) {
   if (!c) return PISLAM_ERR_INVALID_ARG;
   c->use_tma = enable != 0;
+  return PISLAM_OK;
+}
+
+int pislam_b200_set_sub_batch(pislam_ctx* c, int frames) {
+  if (!c || frames < 0) return PISLAM_ERR_INVALID_ARG;
+  c->sub_frames = frames;
   return PISLAM_OK;
 }
 
