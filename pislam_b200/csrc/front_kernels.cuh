@@ -89,6 +89,7 @@ struct FrontParams {
   int log_bucket, bucket_limit;
   int cap;      // record capacity per frame; also the size of the staging overflow region
   int npieces;  // per frame
+  int prefetch_dist;  // CTAs resident on the whole GPU (0: no L2 prefetch of a later CTA's tile)
   int tile_slot;   // staging entries every tile owns (a tile with more survivors reserves in the overflow region)
   int stage_cap;   // staging entries per frame = ntiles * tile_slot + cap
   const TileDesc* tiles;
@@ -273,6 +274,12 @@ __device__ __noinline__ void test_candidate_inline(const uint8_t* s_pix, uint8_t
 #ifndef PB_TASK_LIST
 #define PB_TASK_LIST 1  // phase A compacts non-empty tasks before expanding their bits (0: expand per warp round)
 #endif
+#ifndef PB_A2_ATOMIC
+#define PB_A2_ATOMIC 0  // phase A2: per-lane shared atomics instead of a warp scan + one elected atomic
+#endif
+#ifndef PB_L2_PREFETCH
+#define PB_L2_PREFETCH 0  // every CTA prefetches into L2 the tile a CTA one residency wave later will stage
+#endif
 #ifndef PB_WARP_TAIL
 #define PB_WARP_TAIL 1  // phases D/D2/E of a tile with <= 32 non-zero scores run in warp 0 alone
 #endif
@@ -320,6 +327,21 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(&s_bar, PIX_H * PIX_W);
       tma_load_3d(s_pix, &tmap, x0 - 8 - dxo, L.row_off + y0 - 4, frame, &s_bar);
+#if PB_L2_PREFETCH
+      // CTAs are dispatched in linear order, so the CTA that takes over this CTA's slot is about one residency wave
+      // further on: fetch its tile into L2 now, and its own box load will not wait for DRAM
+      if (P.prefetch_dist > 0) {
+        const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x + (unsigned)P.prefetch_dist;
+        const unsigned fy = lin / gridDim.x, fx = lin - fy * gridDim.x;
+        if (fy < gridDim.y) {
+          const TileDesc nd = P.tiles[fx];
+          const int ndxo = (nd.x0 - 8) & 15;
+          asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(&tmap),
+                       "r"(nd.x0 - 8 - ndxo), "r"(P.lv[nd.level].row_off + nd.y0 - 4), "r"((int)fy)
+                       : "memory");
+        }
+      }
+#endif
     }
   }
   if (tid == 0) {
@@ -391,6 +413,9 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
     }
     __syncthreads();
     if (MODE == MODE_TMA) mbar_wait(&s_bar, 0);
+#if defined(PB_EXPERIMENT_STOP) && PB_EXPERIMENT_STOP == 1
+    return;
+#endif
 
     // ---- phase A: SWAR pre-test on the four compass ring pixels ---------------------------------
     // A 9-arc always contains two neighbouring compass points (ring 1,5,9,13), so a corner needs
@@ -422,6 +447,9 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
       if (acc) s_task[tpos] = make_uint2(acc, (uint32_t)((r0 << 8) | (4 * wx)));
     }
     __syncthreads();
+#if defined(PB_EXPERIMENT_STOP) && PB_EXPERIMENT_STOP == 2
+    return;
+#endif
 
     // ---- phase A2: candidate bits of the non-empty tasks -> list A -----------------------------------
     const int nT = (int)s_nT;  // <= 256 tasks
@@ -435,9 +463,21 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
       if (__ballot_sync(0xffffffffu, acc != 0u) == 0u) continue;  // a warp without candidates (30 %) skips the rest
       const int idx0 = (r0 << 8) | (4 * wx);
 #endif
+      const uint32_t cnt = (uint32_t)__popc(acc);
+#if PB_A2_ATOMIC
+      // every lane reserves its own run: the order of list A is irrelevant (phase B treats candidates alike), and
+      // 32 same-address shared atomics are cheaper than a five-step shuffle scan plus one elected atomic
+      uint32_t pos = 0;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "setp.ne.u32 p, %2, 0;\n\t"
+          "@p atom.shared.add.u32 %0, [%1], %2;\n\t}"
+          : "+r"(pos)
+          : "r"(nA_s), "r"(cnt)
+          : "memory");
+#else
       // one list reservation per warp for all rows
       constexpr uint32_t amask = 0xffffffffu;
-      const uint32_t cnt = (uint32_t)__popc(acc);
       uint32_t incl = cnt;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
@@ -446,6 +486,7 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
       }
       const uint32_t pos0 = warp_atom_shared_add(nA_s, __shfl_sync(0xffffffffu, incl, 31));
       uint32_t pos = pos0 + incl - cnt;
+#endif
       if (pos + cnt <= CAP_A) {
         // 20 predicated stores (a loop over the set bits runs with ~3 of 32 lanes busy); explicit shared
         // addresses: the compiler otherwise rebuilds the shared window base inside every predicated block
@@ -470,6 +511,9 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
       }
     }
     __syncthreads();
+#if defined(PB_EXPERIMENT_STOP) && PB_EXPERIMENT_STOP == 3
+    return;
+#endif
 
     // ---- phase B: exact FAST-9 on the candidates (Fast.h:54-158) ---------------------------------
     const int nA = min((int)s_nA, CAP_A);
@@ -491,6 +535,9 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
       }
     }
     __syncthreads();
+#if defined(PB_EXPERIMENT_STOP) && PB_EXPERIMENT_STOP == 4
+    return;
+#endif
 
     // ---- phase C: Harris code of every flagged pixel (Fast.h:166-180, Harris.h:80-248) ------------
     const int nB = min((int)s_nB, CAP_B);
@@ -541,6 +588,10 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
     atomicOr((lb == 0 ? s_bm : s_occ) + (slot >> 5), 1u << (slot & 31));
     return slot;
   };
+#if defined(PB_EXPERIMENT_STOP)
+  return;  // timing experiment only (results are garbage): PB_EXPERIMENT_STOP = 1 after staging, 2 after phase A,
+           // 3 after A2, 4 after B, 5 after C (no tail)
+#endif
 #if PB_WARP_TAIL
   // A typical tile has a few dozen non-zero scores and keeps a handful of keypoints: one warp finishes it with
   // warp-level synchronisation instead of three more block barriers; the other warps retire.

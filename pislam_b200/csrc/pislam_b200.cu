@@ -158,6 +158,7 @@ struct pislam_ctx {
   long launches = 0;
   int num_sms = 148;
   int orb_tma_ctas_per_sm = 0;  // occupancy of orb_tma_kernel (queried once)
+  int front_resident_ctas = 0;  // CTAs of front_tile_kernel<TMA, 64 rows> resident on the whole GPU (L2 prefetch distance)
   bool use_tma = true;
   EncodeTiledFn encode = nullptr;
   uint32_t* d_brief = nullptr;    // pattern offsets for the 36-byte patch pitch
@@ -201,9 +202,10 @@ struct pislam_ctx {
   int gather_turn = 0;
   // host-buffer batches are pipelined in chunks: H2D (copy_in) | kernels (stream) | D2H (copy_out)
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
-  static const int kMaxChunks = 8;
+  static const int kMaxChunks = 32;
   cudaEvent_t ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {};
   int pipeline_chunks = 4;
+  bool pipeline_chunks_forced = false;  // PISLAM_B200_CHUNKS given: use it for every host source
   size_t l2_chunk_bytes = 48u << 20;  // device-resident base frames: stack bytes built per chunk (stays in the 126 MB L2)
   bool trim_copies = true;
   void* h_rec = nullptr;  // pinned staging for single-frame results
@@ -390,6 +392,7 @@ void fill_front_params(const pislam_ctx* c, FrontParams& P, const uint8_t* src, 
   P.bucket_limit = g.d.bucket_limit;
   P.cap = g.cap;
   P.npieces = g.npieces;
+  P.prefetch_dist = c->front_resident_ctas;
   P.tile_slot = kTileSlot;
   P.stage_cap = g.ntiles * kTileSlot + g.cap;
   P.tiles = g.tiles.as<TileDesc>();
@@ -455,6 +458,14 @@ int enqueue_extract_one(pislam_ctx* c, const uint8_t* d_stacks, size_t frame_str
     static const int pad = getenv("PISLAM_B200_DEBUG_SMEM_PAD") ? atoi(getenv("PISLAM_B200_DEBUG_SMEM_PAD")) : 0;
     const int box_h = g.th == TH_BATCH ? TileCfg<TH_BATCH>::PIX_H : TileCfg<TH_SMALL>::PIX_H;
     const bool tma = tma_ok && make_tensor_map(c, &tmap, d_stacks, d->vstep, g.rows, nframes, frame_stride, PIX_W, box_h) == PISLAM_OK;
+    if (tma && c->front_resident_ctas == 0) {
+      int occ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, front_tile_kernel<MODE_TMA, TH_BATCH>, NT, 0) != cudaSuccess || occ < 1)
+        occ = 1;
+      c->front_resident_ctas = occ * c->num_sms;
+      if (const char* pd = getenv("PISLAM_B200_PREFETCH_DIST")) c->front_resident_ctas = atoi(pd);
+      P.prefetch_dist = c->front_resident_ctas;
+    }
     if (g.th == TH_BATCH) {
       if (tma) front_tile_kernel<MODE_TMA, TH_BATCH><<<grid, NT, pad, c->stream>>>(P, tmap);
       else front_tile_kernel<MODE_LDG, TH_BATCH><<<grid, NT, 0, c->stream>>>(P, tmap);
@@ -748,7 +759,10 @@ int pislam_b200_create(pislam_ctx** out, int device, size_t max_stack_bytes, int
       else if ((e = cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming)) != cudaSuccess) st = -(int)e;
     }
     if (st != PISLAM_OK) break;
-    if (const char* ch = getenv("PISLAM_B200_CHUNKS")) c->pipeline_chunks = std::max(1, std::min(atoi(ch), (int)pislam_ctx::kMaxChunks));
+    if (const char* ch = getenv("PISLAM_B200_CHUNKS")) {
+      c->pipeline_chunks = std::max(1, std::min(atoi(ch), (int)pislam_ctx::kMaxChunks));
+      c->pipeline_chunks_forced = true;
+    }
     if (const char* tr = getenv("PISLAM_B200_TRIM")) c->trim_copies = tr[0] != '0';
     if (const char* l2 = getenv("PISLAM_B200_L2_CHUNK_MB")) c->l2_chunk_bytes = (size_t)std::max(1, atoi(l2)) << 20;
     const char* no_tma = getenv("PISLAM_B200_NO_TMA");
@@ -1219,8 +1233,20 @@ int extract_pipeline(pislam_ctx* c, const FrameSource& src, int nframes, const p
     // chunks: a host source is cut for the copy/compute overlap; device-resident base frames are cut so that a
     // chunk's freshly built stacks are still in L2 when the detector and the descriptor kernel read them
     int per = nframes;
-    if (src_on_host) per = (nframes + std::min(c->pipeline_chunks, nframes) - 1) / std::min(c->pipeline_chunks, nframes);
-    else per = (int)std::max<long long>(1, std::min<long long>(nframes, (long long)c->l2_chunk_bytes / (long long)frame_bytes));
+    if (src_on_host) {
+      // stacks travel as one pitched copy per level and chunk (few, large chunks: 4 measured best); base frames as one
+      // linear copy per chunk, so smaller chunks (~5 MB, at most 16) shorten the un-overlapped head and tail of the
+      // pipeline (profiles/r02_e2e_chunks.txt: 130 -> 148 Gpix/s from 4 to 16 chunks, worse again at 32)
+      int nchunks = c->pipeline_chunks;
+      if (src.base && !c->pipeline_chunks_forced) {
+        const size_t bytes = (size_t)d->widths[0] * d->heights[0] * nframes;
+        nchunks = (int)std::min<size_t>(16, std::max<size_t>(1, bytes / (5u << 20)));
+      }
+      nchunks = std::max(1, std::min(nchunks, nframes));
+      per = (nframes + nchunks - 1) / nchunks;
+    } else {
+      per = (int)std::max<long long>(1, std::min<long long>(nframes, (long long)c->l2_chunk_bytes / (long long)frame_bytes));
+    }
     uint8_t* d_stacks = nullptr;
     const uint8_t* d_bases = src.p;
     int bp = src.pitch;
