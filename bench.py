@@ -335,7 +335,12 @@ def run_gpu_arm(args):
         uid = [api.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(world, rank, uid[0])
-        gather = "one all-gather of the records per step, issued by libpislam_b200 on its second stream"
+        p2p = all([ctx.comm_register(b.data_ptr(), b.numel()) for b in d_alls])
+        gather = ("size-aware exchange: every rank stores the live part of its records straight into the peers' "
+                  "gather buffers over NVLink peer mappings (p2p_push_kernel), on libpislam_b200's second stream"
+                  if p2p else
+                  "one ncclAllGather of the fixed-capacity records per step, issued by libpislam_b200 on its second "
+                  "stream")
     gate = None if args.no_parity else ParityGate(api, bases, F)
 
     def step_device():

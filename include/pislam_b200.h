@@ -33,6 +33,7 @@ extern "C" {
 #define PISLAM_ERR_UNSUPPORTED (-10002) /* geometry outside the fused kernels' domain, see DESIGN.md */
 #define PISLAM_ERR_CAPACITY (-10003)    /* more keypoints than `cap`; *n receives the required count */
 #define PISLAM_ERR_NO_DEVICE (-10004)   /* no CUDA device / wrong architecture */
+#define PISLAM_ERR_PEER_TIMEOUT (-10005) /* a peer rank never reached the record exchange */
 #define PISLAM_ERR_NCCL (-11000)        /* -11000 - ncclResult_t */
 
 #define PISLAM_MAX_LEVELS 16
@@ -199,6 +200,20 @@ int pislam_b200_comm_destroy(pislam_ctx* ctx);
 int pislam_b200_extract_allgather(pislam_ctx* ctx, const uint8_t* d_stacks, size_t frame_stride,
                                   int nframes_local, int slots_per_rank, const pislam_pyramid_desc* desc,
                                   int cap, void* d_all_records);
+
+/* Registers a device buffer for the SIZE-AWARE record exchange (collective: every rank calls it, in the same
+ * order, with a buffer of the same size; 16-byte aligned).  The buffer's allocation is mapped into every peer
+ * (CUDA IPC over NVLink), and pislam_b200_extract_allgather on a gather buffer that lies inside a registered
+ * buffer then moves only the LIVE part of every record -- header, n keypoints, n descriptors, n level bytes --
+ * with a copy kernel that stores straight into the peers' buffers, instead of ncclAllGather on the
+ * fixed-capacity records (~2.4x the bytes at 850 of 2048 slots).  Everything pislam_b200_extract_allgather
+ * promises stays as it is (in-place slots, second stream, alternating buffers); the slack of a record beyond
+ * its n entries is simply not transported.  Returns PISLAM_ERR_UNSUPPORTED -- on every rank alike -- when a
+ * peer mapping is not possible (no IPC, more than 16 ranks, more than 8 buffers): the buffer then keeps working
+ * through ncclAllGather.  Registrations live until pislam_b200_comm_destroy. */
+int pislam_b200_comm_register(pislam_ctx* ctx, void* d_buf, size_t bytes);
+/* Number of buffers registered for the size-aware exchange (0: every gather goes through ncclAllGather). */
+int pislam_b200_comm_p2p_enabled(pislam_ctx* ctx);
 
 /* Makes the ctx stream wait (on the device) for the gathers issued so far by pislam_b200_extract_allgather,
  * so that later work -- or an event recorded -- on the ctx stream is ordered after them. */

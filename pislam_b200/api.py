@@ -18,6 +18,7 @@ PISLAM_ERR_INVALID_ARG = -10001
 PISLAM_ERR_UNSUPPORTED = -10002
 PISLAM_ERR_CAPACITY = -10003
 PISLAM_ERR_NO_DEVICE = -10004
+PISLAM_ERR_PEER_TIMEOUT = -10005
 PISLAM_MAX_LEVELS = 16
 REC_HEADER_WORDS = 32
 
@@ -89,6 +90,8 @@ _SIGNATURES = {
     "pislam_b200_comm_unique_id": (C.c_int, [C.c_void_p]),
     "pislam_b200_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "pislam_b200_comm_destroy": (C.c_int, [C.c_void_p]),
+    "pislam_b200_comm_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "pislam_b200_comm_p2p_enabled": (C.c_int, [C.c_void_p]),
     "pislam_b200_extract_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                                                 C.POINTER(PyramidDesc), C.c_int, C.c_void_p]),
     "pislam_b200_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -440,6 +443,19 @@ class Context:
     def comm_init(self, nranks, rank, unique_id):
         buf = C.create_string_buffer(bytes(unique_id), 128)
         self._ok(self.lib.pislam_b200_comm_init(self._h, nranks, rank, buf))
+
+    def comm_register(self, ptr, nbytes):
+        """Collective: maps the device buffer into every peer for the size-aware exchange.  Returns True when the
+        buffer will use it, False when every rank falls back to ncclAllGather for it."""
+        st = self.lib.pislam_b200_comm_register(self._h, ptr, nbytes)
+        if st == PISLAM_ERR_UNSUPPORTED:
+            return False
+        self._ok(st)
+        return True
+
+    @property
+    def p2p_windows(self):
+        return self.lib.pislam_b200_comm_p2p_enabled(self._h)
 
     def comm_destroy(self):
         self._ok(self.lib.pislam_b200_comm_destroy(self._h))

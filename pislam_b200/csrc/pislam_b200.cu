@@ -23,6 +23,7 @@
 #include "orb_kernels.cuh"
 #include "match_kernels.cuh"
 #include "pyramid_kernels.cuh"
+#include "p2p_gather.cuh"
 
 using namespace pb;
 
@@ -200,6 +201,25 @@ struct pislam_ctx {
     cudaEvent_t done = nullptr;
   } gathers[2];
   int gather_turn = 0;
+  // size-aware exchange over NVLink peer mappings (p2p_gather.cuh): flag block + registered buffers ("windows")
+  struct IpcMap {
+    cudaIpcMemHandle_t handle;
+    int rank;
+    void* base;
+  };
+  struct PeerWindow {
+    uint8_t* local = nullptr;
+    size_t bytes = 0;
+    uint8_t* peer[P2P_MAX_RANKS] = {};
+    uint32_t epoch = 0;
+  };
+  bool p2p_ok = false;
+  uint32_t* d_flags = nullptr;  // this rank's flag block (written by the peers)
+  uint32_t* peer_flags[P2P_MAX_RANKS] = {};
+  int* d_p2p_timeout = nullptr;
+  std::vector<IpcMap> ipc_maps;
+  std::vector<PeerWindow> windows;
+  long p2p_bytes_pushed = 0;  // host-side estimate is impossible (sizes live on the device): see pislam_b200_comm_stats
   // host-buffer batches are pipelined in chunks: H2D (copy_in) | kernels (stream) | D2H (copy_out)
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   static const int kMaxChunks = 32;
@@ -698,6 +718,127 @@ int copy_frames_h2d(pislam_ctx* c, cudaStream_t st, const uint8_t* host, uint8_t
   return PISLAM_OK;
 }
 
+// ---- size-aware exchange over peer mappings (p2p_gather.cuh) ---------------------------------------------------
+typedef CUresult (*MemGetAddressRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+
+// all-gather of a small host blob through the communicator (setup paths only): all[r*bytes ..] = rank r's blob
+int comm_allgather_host(pislam_ctx* c, const void* mine, size_t bytes, std::vector<uint8_t>& all) {
+  all.assign(bytes * (size_t)c->nranks, 0);
+  CK(c->hdr.reserve(bytes * (size_t)c->nranks, false, c->stream));
+  uint8_t* d = c->hdr.as<uint8_t>();
+  CK(cudaMemcpyAsync(d + bytes * (size_t)c->rank, mine, bytes, cudaMemcpyHostToDevice, c->stream));
+  const int r = g_nccl.AllGather(d + bytes * (size_t)c->rank, d, bytes, /*ncclInt8*/ 0, c->comm, c->stream);
+  if (r != 0) return PISLAM_ERR_NCCL - r;
+  CK(cudaMemcpyAsync(all.data(), d, all.size(), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return PISLAM_OK;
+}
+
+// maps a peer's allocation (once per handle and rank)
+int ipc_open(pislam_ctx* c, const cudaIpcMemHandle_t& h, int rank, void** base) {
+  for (const pislam_ctx::IpcMap& m : c->ipc_maps)
+    if (m.rank == rank && memcmp(&m.handle, &h, sizeof(h)) == 0) {
+      *base = m.base;
+      return PISLAM_OK;
+    }
+  void* p = nullptr;
+  const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return -(int)e;
+  }
+  pislam_ctx::IpcMap m;
+  m.handle = h;
+  m.rank = rank;
+  m.base = p;
+  c->ipc_maps.push_back(m);
+  *base = p;
+  return PISLAM_OK;
+}
+
+struct IpcBlob {
+  cudaIpcMemHandle_t handle;
+  unsigned long long offset, bytes;
+  int ok;
+};
+
+// base allocation + offset of a device pointer (IPC handles describe whole allocations)
+bool ipc_describe(const void* ptr, size_t bytes, IpcBlob* b) {
+  memset(b, 0, sizeof(*b));
+  static MemGetAddressRangeFn get_range = nullptr;
+  if (!get_range) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) != cudaSuccess ||
+        qr != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    get_range = reinterpret_cast<MemGetAddressRangeFn>(fn);
+  }
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (get_range(&base, &size, (CUdeviceptr)(uintptr_t)ptr) != CUDA_SUCCESS) return false;
+  if (cudaIpcGetMemHandle(&b->handle, reinterpret_cast<void*>((uintptr_t)base)) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  b->offset = (unsigned long long)((uintptr_t)ptr - (uintptr_t)base);
+  b->bytes = bytes;
+  b->ok = 1;
+  return true;
+}
+
+// the flag block every peer writes its READY / DONE epochs into; collective (called from comm_init)
+int p2p_setup(pislam_ctx* c) {
+  c->p2p_ok = false;
+  if (c->nranks < 2 || c->nranks > P2P_MAX_RANKS) return PISLAM_OK;
+  const size_t fbytes = (size_t)P2P_MAX_WINDOWS * 2 * P2P_MAX_RANKS * 4;
+  IpcBlob mine;
+  memset(&mine, 0, sizeof(mine));
+  if (getenv("PISLAM_B200_NO_P2P") == nullptr && cudaMalloc(&c->d_flags, fbytes) == cudaSuccess &&
+      cudaMalloc(&c->d_p2p_timeout, 4) == cudaSuccess) {
+    cudaMemset(c->d_flags, 0, fbytes);
+    cudaMemset(c->d_p2p_timeout, 0, 4);
+    ipc_describe(c->d_flags, fbytes, &mine);
+  } else {
+    cudaGetLastError();
+  }
+  std::vector<uint8_t> all;
+  CKS(comm_allgather_host(c, &mine, sizeof(mine), all));
+  bool ok = true;
+  for (int r = 0; r < c->nranks; ++r) ok = ok && reinterpret_cast<const IpcBlob*>(all.data() + r * sizeof(IpcBlob))->ok;
+  int opened = ok ? 1 : 0;
+  if (ok)
+    for (int r = 0; r < c->nranks && opened; ++r) {
+      const IpcBlob* b = reinterpret_cast<const IpcBlob*>(all.data() + r * sizeof(IpcBlob));
+      if (r == c->rank) {
+        c->peer_flags[r] = c->d_flags;
+        continue;
+      }
+      void* base = nullptr;
+      if (ipc_open(c, b->handle, r, &base) != PISLAM_OK) opened = 0;
+      else c->peer_flags[r] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(base) + b->offset);
+    }
+  // every rank must agree, or some would wait in NCCL and others on flags
+  CKS(comm_allgather_host(c, &opened, sizeof(opened), all));
+  for (int r = 0; r < c->nranks; ++r) opened = opened && *reinterpret_cast<const int*>(all.data() + r * sizeof(int));
+  c->p2p_ok = opened != 0;
+  return PISLAM_OK;
+}
+
+void p2p_teardown(pislam_ctx* c) {
+  for (const pislam_ctx::IpcMap& m : c->ipc_maps) cudaIpcCloseMemHandle(m.base);
+  c->ipc_maps.clear();
+  c->windows.clear();
+  if (c->d_flags) cudaFree(c->d_flags);
+  if (c->d_p2p_timeout) cudaFree(c->d_p2p_timeout);
+  c->d_flags = nullptr;
+  c->d_p2p_timeout = nullptr;
+  c->p2p_ok = false;
+  cudaGetLastError();
+}
+
 // after a sync: PISLAM_ERR_CAPACITY if any frame found more keypoints than it stored
 int check_capacity(pislam_ctx* c, const uint8_t* d_records, int nframes, size_t rec_bytes) {
   std::vector<uint32_t> h((size_t)nframes * 2);
@@ -816,6 +957,7 @@ int pislam_b200_destroy(pislam_ctx* c) {
   if (c->copy_in) cudaStreamSynchronize(c->copy_in);
   if (c->copy_out) cudaStreamSynchronize(c->copy_out);
   if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
+  p2p_teardown(c);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   DevBuf* bufs[] = {&c->img, &c->out, &c->kp, &c->desc, &c->aux0, &c->aux1, &c->stage, &c->stage_count,
                     &c->piece_cnt, &c->piece_off, &c->stacks, &c->records, &c->hdr};
@@ -856,6 +998,7 @@ const char* pislam_b200_error_string(int status) {
     case PISLAM_ERR_UNSUPPORTED: return "geometry or parameters outside the supported domain";
     case PISLAM_ERR_CAPACITY: return "keypoint capacity exceeded";
     case PISLAM_ERR_NO_DEVICE: return "no usable sm_100 CUDA device";
+    case PISLAM_ERR_PEER_TIMEOUT: return "a peer rank never reached the record exchange (10 s)";
     default: break;
   }
   if (status <= PISLAM_ERR_NCCL) return "NCCL error";
@@ -869,6 +1012,11 @@ int pislam_b200_synchronize(pislam_ctx* c) {
   if (!c) return PISLAM_ERR_INVALID_ARG;
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaStreamSynchronize(c->comm_stream));
+  if (c->d_p2p_timeout) {
+    int t = 0;
+    CK(cudaMemcpy(&t, c->d_p2p_timeout, 4, cudaMemcpyDeviceToHost));
+    if (t) return PISLAM_ERR_PEER_TIMEOUT;
+  }
   return PISLAM_OK;
 }
 
@@ -1443,7 +1591,7 @@ int pislam_b200_comm_init(pislam_ctx* c, int nranks, int rank, const void* id128
   }
   c->nranks = nranks;
   c->rank = rank;
-  return PISLAM_OK;
+  return p2p_setup(c);  // collective: the flag blocks of the size-aware exchange (falls back to NCCL when IPC is unavailable)
 }
 
 int pislam_b200_comm_destroy(pislam_ctx* c) {
@@ -1452,6 +1600,7 @@ int pislam_b200_comm_destroy(pislam_ctx* c) {
     CKS(set_device(c));
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->comm_stream);
+    p2p_teardown(c);
     g_nccl.CommDestroy(c->comm);
     c->comm = nullptr;
   }
@@ -1459,6 +1608,43 @@ int pislam_b200_comm_destroy(pislam_ctx* c) {
   c->rank = 0;
   return PISLAM_OK;
 }
+
+int pislam_b200_comm_register(pislam_ctx* c, void* d_buf, size_t bytes) {
+  if (!c || !d_buf || bytes == 0 || (reinterpret_cast<uintptr_t>(d_buf) & 15) != 0) return PISLAM_ERR_INVALID_ARG;
+  if (!c->comm) return PISLAM_ERR_NCCL;
+  CKS(set_device(c));
+  // collective even when this rank cannot take part: every rank learns the common verdict
+  IpcBlob mine;
+  memset(&mine, 0, sizeof(mine));
+  if (c->p2p_ok && (int)c->windows.size() < P2P_MAX_WINDOWS && is_device_ptr(d_buf)) ipc_describe(d_buf, bytes, &mine);
+  std::vector<uint8_t> all;
+  CKS(comm_allgather_host(c, &mine, sizeof(mine), all));
+  int ok = 1;
+  for (int r = 0; r < c->nranks; ++r) {
+    const IpcBlob* b = reinterpret_cast<const IpcBlob*>(all.data() + r * sizeof(IpcBlob));
+    ok = ok && b->ok && b->bytes == bytes;
+  }
+  pislam_ctx::PeerWindow w;
+  w.local = static_cast<uint8_t*>(d_buf);
+  w.bytes = bytes;
+  for (int r = 0; r < c->nranks && ok; ++r) {
+    const IpcBlob* b = reinterpret_cast<const IpcBlob*>(all.data() + r * sizeof(IpcBlob));
+    if (r == c->rank) {
+      w.peer[r] = w.local;
+      continue;
+    }
+    void* base = nullptr;
+    if (ipc_open(c, b->handle, r, &base) != PISLAM_OK) ok = 0;
+    else w.peer[r] = static_cast<uint8_t*>(base) + b->offset;
+  }
+  CKS(comm_allgather_host(c, &ok, sizeof(ok), all));
+  for (int r = 0; r < c->nranks; ++r) ok = ok && *reinterpret_cast<const int*>(all.data() + r * sizeof(int));
+  if (!ok) return PISLAM_ERR_UNSUPPORTED;  // on every rank alike: the buffer keeps working through ncclAllGather
+  c->windows.push_back(w);
+  return PISLAM_OK;
+}
+
+int pislam_b200_comm_p2p_enabled(pislam_ctx* c) { return (c && c->p2p_ok) ? (int)c->windows.size() : 0; }
 
 int pislam_b200_extract_allgather(pislam_ctx* c, const uint8_t* d_stacks, size_t frame_stride, int nframes_local,
                                   int slots_per_rank, const pislam_pyramid_desc* d, int cap, void* d_all_records) {
@@ -1468,12 +1654,19 @@ int pislam_b200_extract_allgather(pislam_ctx* c, const uint8_t* d_stacks, size_t
   if (!c->comm) return PISLAM_ERR_NCCL;
   CKS(set_device(c));
   // everything that can fail on this rank alone is checked BEFORE any work is enqueued: once the kernels are
-  // in flight the collective is issued unconditionally, so no peer is left waiting in ncclAllGather
+  // in flight the exchange is issued unconditionally, so no peer is left waiting
   CKS(validate_desc(d, cap, true));
-  const size_t rec_bytes = RecordLayout::make(cap, d->words).bytes;
+  const RecordLayout rec = RecordLayout::make(cap, d->words);
+  const size_t rec_bytes = rec.bytes;
   const size_t slot = rec_bytes * (size_t)slots_per_rank;
   // the kernels write this rank's records straight into its slot of the gather buffer (in-place gather)
-  uint8_t* mine = static_cast<uint8_t*>(d_all_records) + slot * (size_t)c->rank;
+  uint8_t* all = static_cast<uint8_t*>(d_all_records);
+  uint8_t* mine = all + slot * (size_t)c->rank;
+  // a buffer registered with pislam_b200_comm_register takes the size-aware exchange over peer mappings
+  int win = -1;
+  for (size_t i = 0; i < c->windows.size(); ++i)
+    if (all >= c->windows[i].local && all + slot * (size_t)c->nranks <= c->windows[i].local + c->windows[i].bytes)
+      win = (int)i;
   // a gather that is still filling this buffer must finish before the kernels write into it again; with two
   // alternating buffers the previous gather (other buffer) keeps running under this batch's kernels
   pislam_ctx::GatherSlot& g = c->gathers[c->gather_turn];
@@ -1486,6 +1679,20 @@ int pislam_b200_extract_allgather(pislam_ctx* c, const uint8_t* d_stacks, size_t
   // a third buffer evicts the older entry: from then on nothing remembers that entry's gather, so order this
   // call (and through the stream everything later) behind it
   if (!known && g.ptr) CK(cudaStreamWaitEvent(c->stream, g.done, 0));
+  P2pPeers peers;
+  memset(&peers, 0, sizeof(peers));
+  uint32_t epoch = 0;
+  if (win >= 0) {
+    pislam_ctx::PeerWindow& w = c->windows[win];
+    epoch = ++w.epoch;
+    for (int r = 0; r < c->nranks; ++r) {
+      peers.buf[r] = w.peer[r] + (all - w.local);
+      peers.flags[r] = c->peer_flags[r];
+    }
+    // READY(e): from here on the peers may overwrite their slots of this rank's buffer
+    p2p_flag_kernel<<<1, 32, 0, c->stream>>>(peers, c->nranks, c->rank, win, P2P_READY, epoch);
+    CKS(check_launch(c));
+  }
   int st = enqueue_extract(c, d_stacks, frame_stride, nframes_local, d, cap, mine);
   // a ragged shard leaves trailing slots unused: their headers read "no keypoints" (n = n_total = 0, level starts 0)
   if (st == PISLAM_OK && nframes_local < slots_per_rank) {
@@ -1496,8 +1703,28 @@ int pislam_b200_extract_allgather(pislam_ctx* c, const uint8_t* d_stacks, size_t
   cudaError_t e = cudaEventRecord(c->ev_extract, c->stream);
   if (e == cudaSuccess) e = cudaStreamWaitEvent(c->comm_stream, c->ev_extract, 0);
   if (e != cudaSuccess && st == PISLAM_OK) st = -(int)e;
-  const int r = g_nccl.AllGather(mine, d_all_records, slot, /*ncclInt8*/ 0, c->comm, c->comm_stream);
-  if (r != 0) return PISLAM_ERR_NCCL - r;
+  if (win >= 0) {
+    P2pPushParams Q;
+    memset(&Q, 0, sizeof(Q));
+    Q.peers = peers;
+    Q.nranks = c->nranks;
+    Q.rank = c->rank;
+    Q.slots_per_rank = slots_per_rank;
+    Q.slot_offset = slot * (size_t)c->rank;
+    Q.rec = rec;
+    Q.words = d->words;
+    Q.cap = cap;
+    p2p_wait_kernel<<<1, 32, 0, c->comm_stream>>>(c->d_flags, c->nranks, c->rank, win, P2P_READY, epoch, c->d_p2p_timeout);
+    p2p_push_kernel<<<dim3(slots_per_rank, c->nranks - 1), 256, 0, c->comm_stream>>>(Q);
+    p2p_flag_kernel<<<1, 32, 0, c->comm_stream>>>(peers, c->nranks, c->rank, win, P2P_DONE, epoch);
+    p2p_wait_kernel<<<1, 32, 0, c->comm_stream>>>(c->d_flags, c->nranks, c->rank, win, P2P_DONE, epoch, c->d_p2p_timeout);
+    c->launches += 3;
+    const int ls = check_launch(c);
+    if (ls != PISLAM_OK && st == PISLAM_OK) st = ls;
+  } else {
+    const int r = g_nccl.AllGather(mine, d_all_records, slot, /*ncclInt8*/ 0, c->comm, c->comm_stream);
+    if (r != 0) return PISLAM_ERR_NCCL - r;
+  }
   c->gather_turn ^= 1;
   g.ptr = d_all_records;
   CK(cudaEventRecord(g.done, c->comm_stream));

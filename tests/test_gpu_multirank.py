@@ -4,7 +4,9 @@ stream) and EVERY rank must end up with all frames' records, bit-exact against t
 ragged shards (5 frames over 2 ranks, 11 over 8) and empty shards (1 frame over 2 ranks, 3 over 8: trailing ranks own
 nothing and still take part), alternating gather buffers (the overlapped form bench.py times), the same buffer twice
 in a row, a third buffer (eviction of the tracked gather), and pislam_b200_extract_batch + the stand-alone
-pislam_b200_allgather.  Runs at 2 ranks and at 8 ranks; each is skipped when the box has fewer GPUs:
+pislam_b200_allgather.  Buffers 0 and 1 are registered with pislam_b200_comm_register and take the size-aware
+exchange over NVLink peer mappings (only the live part of every record travels), buffer 2 is not and goes through
+ncclAllGather: both must deliver the same records.  Runs at 2 ranks and at 8 ranks; each is skipped when the box has fewer GPUs:
 `gpurun --gpus 8 -- python -m pytest tests/test_gpu_multirank.py -m gpu`."""
 import os
 import sys
@@ -42,13 +44,25 @@ def worker(rank, world, port, frame_counts, out):
     want = [oracle.extract_pyramid(s, VGA.widths, VGA.heights, VGA.row_offsets, log_bucket=4, bucket_limit=3)
             for s in all_stacks]
     failures = []
+    # gather buffers for the largest case, alive for the whole test: 0 and 1 registered for the peer-mapped exchange
+    max_per = max(sharding.frames_per_rank(n, world) for n in frame_counts)
+    big = [torch.empty(world * max_per * rec_bytes, dtype=torch.uint8, device="cuda") for _ in range(3)]
+    registered = [ctx.comm_register(b.data_ptr(), b.numel()) for b in big[:2]]
+    if os.environ.get("PISLAM_B200_NO_P2P") is None and not all(registered):
+        failures.append("comm_register fell back to NCCL: %s" % registered)
+    if ctx.p2p_windows != sum(registered):
+        failures.append("p2p_windows %d vs %s" % (ctx.p2p_windows, registered))
 
     for nframes in frame_counts:
         per = sharding.frames_per_rank(nframes, world)
         start, count = sharding.shard_frames(nframes, world, rank)
         stacks = np.stack(all_stacks[start:start + count]) if count else np.zeros((1, VGA.rows, VGA.vstep), np.uint8)
         d_stacks = torch.from_numpy(stacks).cuda()
-        bufs = [torch.full((world * per * rec_bytes,), 0xA5, dtype=torch.uint8, device="cuda") for _ in range(3)]
+        bufs = [b[:world * per * rec_bytes] for b in big]
+        for b in bufs:
+            b.fill_(0xA5)
+        torch.cuda.synchronize()
+        dist.barrier()  # nobody pushes into a buffer a slower rank is still filling with 0xA5
 
         def check(buf, what):
             recs = api.parse_records(buf.cpu().numpy(), world * per, CAP, WORDS)
@@ -79,6 +93,7 @@ def worker(rank, world, port, frame_counts, out):
         # (2) the same buffer twice in a row (the second extraction must wait for the first gather), then a third
         # buffer (evicts the older tracked gather) and back
         bufs[0].fill_(0x5A)
+        torch.cuda.synchronize()  # the fill runs on torch's stream, the exchange on the library's
         for b in (0, 0, 2, 1, 0):
             extract(bufs[b])
         ctx.synchronize()
@@ -88,6 +103,7 @@ def worker(rank, world, port, frame_counts, out):
         # pislam_b200_allgather moves whole slots and knows nothing about unused ones)
         if nframes == world * per:
             bufs[1].zero_()
+            torch.cuda.synchronize()
             slot = bufs[1][rank * per * rec_bytes:(rank + 1) * per * rec_bytes]
             st = ctx.extract_batch_ptr(stacks.ctypes.data, VGA.stack_bytes, count, desc, CAP, slot.data_ptr())
             st2 = ctx.allgather_ptr(bufs[1].data_ptr(), per * rec_bytes)
@@ -95,6 +111,7 @@ def worker(rank, world, port, frame_counts, out):
             if st != 0 or st2 != 0:
                 failures.append("%d frames: extract_batch %d / allgather %d" % (nframes, st, st2))
             check(bufs[1], "extract_batch + allgather")
+        ctx.synchronize()
         dist.barrier()
         del bufs, d_stacks
     out[rank] = failures
