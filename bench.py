@@ -323,7 +323,8 @@ def run_gpu_arm(args):
     h_records = torch.empty(F * rec_bytes, dtype=torch.uint8, pin_memory=True)
     d_stacks = h_stacks.to("cuda", non_blocking=False)
     # two gather buffers: the all-gather of step k runs under the kernels of step k+1
-    d_alls = [torch.zeros(world * F * rec_bytes, dtype=torch.uint8, device="cuda") for _ in range(2 if world > 1 else 1)]
+    nbufs = max(2, int(os.environ.get("PISLAM_BENCH_GATHER_BUFS", "2"))) if world > 1 else 1
+    d_alls = [torch.zeros(world * F * rec_bytes, dtype=torch.uint8, device="cuda") for _ in range(nbufs)]
     d_all = d_alls[0]
     d_records = d_all[rank * F * rec_bytes:(rank + 1) * F * rec_bytes]
     turn = [0]
@@ -347,7 +348,7 @@ def run_gpu_arm(args):
         """inputs resident in HBM; results (this rank's records, all-gathered when N>1) left in HBM"""
         if world > 1:
             buf = d_alls[turn[0]]
-            turn[0] ^= 1
+            turn[0] = (turn[0] + 1) % len(d_alls)
             st = ctx.extract_allgather_ptr(d_stacks.data_ptr(), frame_bytes, F, desc, CAP, buf.data_ptr())
         else:
             st = ctx.extract_batch_ptr(d_stacks.data_ptr(), frame_bytes, F, desc, CAP, d_records.data_ptr(),
@@ -367,15 +368,23 @@ def run_gpu_arm(args):
             with torch.cuda.stream(stream):
                 h_records.copy_(d_records, non_blocking=True)
 
-    def step_e2e():
-        """the call a user makes: HOST stacks in, HOST records out (H2D + kernels + D2H inside the call)"""
+    def step_e2e(asynchronous=True):
+        """the call a user makes: HOST stacks in, HOST records out (H2D + kernels + D2H inside the call).  The
+        issue-only form (pislam_b200_extract_batch_async on pinned host buffers) lets consecutive calls overlap: the
+        H2D of step k+1 runs under the kernels and the D2H of step k; the timed region ends after the last D2H."""
         dst = h_records.data_ptr() if world == 1 else d_records.data_ptr()
-        e2e_tail(ctx.extract_batch_ptr(h_stacks.data_ptr(), frame_bytes, F, desc, CAP, dst))
+        e2e_tail(ctx.extract_batch_ptr(h_stacks.data_ptr(), frame_bytes, F, desc, CAP, dst, asynchronous=asynchronous))
 
-    def step_e2e_base():
+    def step_e2e_blocking():
+        step_e2e(False)
+
+    def step_e2e_base(asynchronous=True):
         """HOST base frames in, HOST records out: the pyramid is built on the GPU"""
         dst = h_records.data_ptr() if world == 1 else d_records.data_ptr()
-        e2e_tail(ctx.extract_frames_ptr(h_bases.data_ptr(), W, W * H, F, desc, CAP, dst))
+        e2e_tail(ctx.extract_frames_ptr(h_bases.data_ptr(), W, W * H, F, desc, CAP, dst, asynchronous=asynchronous))
+
+    def step_e2e_base_blocking():
+        step_e2e_base(False)
 
     def barrier():
         if world > 1:
@@ -442,6 +451,11 @@ def run_gpu_arm(args):
     ms_e2e, _, _, _ = timed(step_e2e, args.steps)
     if gate:
         gate.check_records("e2e_host_records", h_records.numpy())
+    h_records.zero_()
+    ms_e2e_blk, _, _, _ = timed(step_e2e_blocking, max(3, args.steps // 2))
+    ms_e2e_blk *= args.steps / max(3, args.steps // 2)
+    if gate:
+        gate.check_records("e2e_blocking_host_records", h_records.numpy())
 
     for _ in range(W_):
         step_e2e_base()
@@ -449,6 +463,8 @@ def run_gpu_arm(args):
     ms_e2e_base, launches_base, _, _ = timed(step_e2e_base, args.steps)
     if gate:
         gate.check_records("e2e_base_frames_host_records", h_records.numpy())
+    ms_e2e_base_blk, _, _, _ = timed(step_e2e_base_blocking, max(3, args.steps // 2))
+    ms_e2e_base_blk *= args.steps / max(3, args.steps // 2)
 
     # roofline of the dominant kernel: per-kernel CUDA events (library profiling mode), same inputs
     roof = latency = demo_ms = base_dev = None
@@ -497,12 +513,20 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": F * LAY.level_pixels,
                     "h2d_note": "level pixels only: the padding right of each level is not uploaded",
                     "d2h_bytes_per_step": F * rec_bytes, "ms_per_step": ms_e2e / args.steps,
-                    "keypoints_per_s": kpts_total * args.steps / (ms_e2e * 1e-3)},
+                    "keypoints_per_s": kpts_total * args.steps / (ms_e2e * 1e-3),
+                    "call": "pislam_b200_extract_batch_async on pinned host buffers, steps issued back to back "
+                            "(the copies of consecutive calls overlap), timed until the last D2H has landed",
+                    "blocking_call": {"value": pix * args.steps / (ms_e2e_blk * 1e-3) / 1e6, "unit": UNIT,
+                                      "ms_per_step": ms_e2e_blk / args.steps,
+                                      "call": "pislam_b200_extract_batch, one blocking call per step"}},
             "e2e_base_frames": {"value": e2e_base_value, "unit": UNIT, "h2d_bytes_per_step": F * W * H,
                                 "d2h_bytes_per_step": F * rec_bytes, "ms_per_step": ms_e2e_base / args.steps,
                                 "note": "host BASE frames in, host records out: pislam_b200_extract_frames builds "
                                         "the 8-level pyramid on the GPU; Mpix/s over the same level pixels",
-                                "gpu_launches": launches_base, "device_resident": base_dev},
+                                "gpu_launches": launches_base, "device_resident": base_dev,
+                                "call": "pislam_b200_extract_frames_async, steps issued back to back",
+                                "blocking_call": {"value": pix * args.steps / (ms_e2e_base_blk * 1e-3) / 1e6,
+                                                  "unit": UNIT, "ms_per_step": ms_e2e_base_blk / args.steps}},
             "gpu_launches": launches,
             "single_frame_latency_us": latency,
             "literal_stage_demo_loop_ms_per_frame": demo_ms,

@@ -47,7 +47,7 @@ int pislam_b200_destroy(pislam_ctx* ctx);
 const char* pislam_b200_error_string(int status);
 /* The CUDA stream (cudaStream_t) all work of this ctx is issued on. */
 void* pislam_b200_stream(pislam_ctx* ctx);
-/* Blocks until everything issued on the ctx stream has finished. */
+/* Blocks until everything this ctx has issued has finished (kernels, copies of the host pipelines, exchanges). */
 int pislam_b200_synchronize(pislam_ctx* ctx);
 /* Number of kernel launches issued by this ctx since creation (bench.py's gpu_launches). */
 long pislam_b200_launch_count(pislam_ctx* ctx);
@@ -148,10 +148,15 @@ size_t pislam_b200_record_level_offset(int cap, int words);
 int pislam_b200_extract_batch(pislam_ctx* ctx, const uint8_t* stacks, size_t frame_stride, int nframes,
                               const pislam_pyramid_desc* desc, int cap, void* records);
 
-/* Same, issue only: returns after enqueueing on the ctx stream (device-resident inputs and
- * outputs only).  Capacity overflow is reported by header[1] > header[0]. */
-int pislam_b200_extract_batch_async(pislam_ctx* ctx, const uint8_t* d_stacks, size_t frame_stride,
-                                    int nframes, const pislam_pyramid_desc* desc, int cap, void* d_records);
+/* Same, issue only: returns after enqueueing (nothing waits for the device); pislam_b200_synchronize waits for
+ * everything, records on the host included.  Capacity overflow is reported by header[1] > header[0] of a frame.
+ * Device stacks and device records: the kernels are enqueued on the ctx stream.  Host buffers (pinned memory, or
+ * the copies are not asynchronous): the chunked H2D | kernels | D2H pipeline of pislam_b200_extract_batch with
+ * double-buffered device staging, so consecutive calls overlap -- the H2D of call k+1 runs under the kernels and
+ * the D2H of call k, and the copy engine never idles between calls.  The caller must not reuse a host records
+ * buffer before the call that fills it has completed. */
+int pislam_b200_extract_batch_async(pislam_ctx* ctx, const uint8_t* stacks, size_t frame_stride,
+                                    int nframes, const pislam_pyramid_desc* desc, int cap, void* records);
 
 /* Single pyramid convenience wrapper over extract_batch that scatters the record into the
  * caller's arrays (host pointers; kp_level / desc may be NULL). */
@@ -181,6 +186,10 @@ int pislam_b200_build_pyramid(pislam_ctx* ctx, const uint8_t* frames, int frame_
  * stacks build_pyramid would produce. */
 int pislam_b200_extract_frames(pislam_ctx* ctx, const uint8_t* frames, int frame_pitch, size_t frame_stride,
                                int nframes, int blur, const pislam_pyramid_desc* desc, int cap, void* records);
+
+/* issue-only form of pislam_b200_extract_frames (see pislam_b200_extract_batch_async) */
+int pislam_b200_extract_frames_async(pislam_ctx* ctx, const uint8_t* frames, int frame_pitch, size_t frame_stride,
+                                     int nframes, int blur, const pislam_pyramid_desc* desc, int cap, void* records);
 
 /* ---- multi-GPU: frames shard one-per-rank, results meet in ONE all-gather --------------------- */
 /* 128-byte ncclUniqueId; create on rank 0, distribute with any host-side channel. */
@@ -215,8 +224,9 @@ int pislam_b200_comm_register(pislam_ctx* ctx, void* d_buf, size_t bytes);
 /* Number of buffers registered for the size-aware exchange (0: every gather goes through ncclAllGather). */
 int pislam_b200_comm_p2p_enabled(pislam_ctx* ctx);
 
-/* Makes the ctx stream wait (on the device) for the gathers issued so far by pislam_b200_extract_allgather,
- * so that later work -- or an event recorded -- on the ctx stream is ordered after them. */
+/* Makes the ctx stream wait (on the device) for the gathers issued so far by pislam_b200_extract_allgather and
+ * for the record copies of the issue-only host pipelines (pislam_b200_extract_*_async), so that later work --
+ * or an event recorded -- on the ctx stream is ordered after them. */
 int pislam_b200_join(pislam_ctx* ctx);
 /* In-place ncclAllGather on the ctx stream of a rank-major buffer whose slot `rank` (bytes_per_rank
  * bytes) this rank has already filled, e.g. with pislam_b200_extract_batch on device records. */

@@ -85,6 +85,8 @@ _SIGNATURES = {
                                             C.c_int, C.c_void_p]),
     "pislam_b200_extract_batch_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
                                                   C.POINTER(PyramidDesc), C.c_int, C.c_void_p]),
+    "pislam_b200_extract_frames_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_int,
+                                                   C.POINTER(PyramidDesc), C.c_int, C.c_void_p]),
     "pislam_b200_extract_pyramid": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(PyramidDesc), _u32p, _u8p, _u32p,
                                               C.c_int, _intp]),
     "pislam_b200_comm_unique_id": (C.c_int, [C.c_void_p]),
@@ -429,10 +431,12 @@ class Context:
             self._ok(st)
         return parse_records(rec, nf, cap, desc.words)
 
-    def extract_frames_ptr(self, frames_ptr, frame_pitch, frame_stride, nframes, desc, cap, records_ptr, blur=False):
-        """Raw-pointer form (host or device memory)."""
-        return self.lib.pislam_b200_extract_frames(self._h, frames_ptr, frame_pitch, frame_stride, nframes,
-                                                   int(bool(blur)), C.byref(desc), cap, records_ptr)
+    def extract_frames_ptr(self, frames_ptr, frame_pitch, frame_stride, nframes, desc, cap, records_ptr, blur=False,
+                           asynchronous=False):
+        """Raw-pointer form (host or device memory); asynchronous=True only enqueues (see synchronize())."""
+        f = self.lib.pislam_b200_extract_frames_async if asynchronous else self.lib.pislam_b200_extract_frames
+        return f(self._h, frames_ptr, frame_pitch, frame_stride, nframes, int(bool(blur)), C.byref(desc), cap,
+                 records_ptr)
 
     def extract_batch_ptr(self, stacks_ptr, frame_stride, nframes, desc, cap, records_ptr, asynchronous=False):
         """Raw-pointer form (host or device memory, e.g. torch tensors' data_ptr())."""

@@ -59,6 +59,22 @@ struct DevBuf {
     if (zero_new) e = cudaMemsetAsync(p, 0, want, st);
     return e;
   }
+  // for buffers used from several streams: growing waits for the whole device
+  cudaError_t reserve_any(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) {
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) return e;
+      cudaFree(p);
+      p = nullptr;
+      cap = 0;
+    }
+    const size_t want = ((n + (n >> 2) + 4095) & ~(size_t)4095) + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) return e;
+    cap = want;
+    return cudaSuccess;
+  }
   void release() {
     if (p) cudaFree(p);
     p = nullptr;
@@ -186,6 +202,12 @@ struct pislam_ctx {
   static const int kPyrCache = 4;
   PyrTables pyr[kPyrCache];
   DevBuf bases, blur_tmp, blur_out;
+  // double-buffered device staging of the host-source pipeline (pipeline_enqueue)
+  struct Staging {
+    DevBuf stacks, bases, records;
+    cudaEvent_t src_free = nullptr, rec_free = nullptr;
+  } staging[2];
+  int stage_turn = 0;
   // multi-GPU: the all-gather runs on its own stream so that it overlaps the next batch's kernels
   NcclComm comm = nullptr;
   int nranks = 1, rank = 0;
@@ -196,10 +218,11 @@ struct pislam_ctx {
   cudaStream_t orb_stream = nullptr;
   cudaEvent_t ev_sub = nullptr, ev_orb = nullptr;
   int sub_frames = 0;  // frames per sub-batch (0: the whole call in one piece)
+  static const int kGatherSlots = 4;
   struct GatherSlot {
     void* ptr = nullptr;  // gather buffer last used with this event
     cudaEvent_t done = nullptr;
-  } gathers[2];
+  } gathers[kGatherSlots];  // the last few gather buffers (round robin): a caller may rotate up to that many
   int gather_turn = 0;
   // size-aware exchange over NVLink peer mappings (p2p_gather.cuh): flag block + registered buffers ("windows")
   struct IpcMap {
@@ -889,10 +912,15 @@ int pislam_b200_create(pislam_ctx** out, int device, size_t max_stack_bytes, int
       if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) prio_hi = 0;
       if ((e = cudaStreamCreateWithPriority(&c->orb_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) { st = -(int)e; break; }
     }
+    for (int i = 0; i < 2 && st == PISLAM_OK; ++i) {
+      if ((e = cudaEventCreateWithFlags(&c->staging[i].src_free, cudaEventDisableTiming)) != cudaSuccess) st = -(int)e;
+      else if ((e = cudaEventCreateWithFlags(&c->staging[i].rec_free, cudaEventDisableTiming)) != cudaSuccess) st = -(int)e;
+    }
+    if (st != PISLAM_OK) break;
     if ((e = cudaEventCreateWithFlags(&c->ev_sub, cudaEventDisableTiming)) != cudaSuccess) { st = -(int)e; break; }
     if ((e = cudaEventCreateWithFlags(&c->ev_orb, cudaEventDisableTiming)) != cudaSuccess) { st = -(int)e; break; }
     if (const char* sf = getenv("PISLAM_B200_SUB_FRAMES")) c->sub_frames = std::max(0, atoi(sf));
-    for (int i = 0; i < 2 && st == PISLAM_OK; ++i)
+    for (int i = 0; i < pislam_ctx::kGatherSlots && st == PISLAM_OK; ++i)
       if ((e = cudaEventCreateWithFlags(&c->gathers[i].done, cudaEventDisableTiming)) != cudaSuccess) st = -(int)e;
     if (st != PISLAM_OK) break;
     for (int i = 0; i < pislam_ctx::kMaxChunks && st == PISLAM_OK; ++i) {
@@ -963,6 +991,13 @@ int pislam_b200_destroy(pislam_ctx* c) {
                     &c->piece_cnt, &c->piece_off, &c->stacks, &c->records, &c->hdr};
   for (DevBuf* b : bufs) b->release();
   for (Geometry& e : c->geos) e.tiles.release();
+  for (pislam_ctx::Staging& st_ : c->staging) {
+    st_.stacks.release();
+    st_.bases.release();
+    st_.records.release();
+    if (st_.src_free) cudaEventDestroy(st_.src_free);
+    if (st_.rec_free) cudaEventDestroy(st_.rec_free);
+  }
   for (pislam_ctx::PyrTables& e : c->pyr) e.taps.release();
   c->bases.release();
   c->blur_tmp.release();
@@ -981,7 +1016,7 @@ int pislam_b200_destroy(pislam_ctx* c) {
     cudaStreamSynchronize(c->orb_stream);
     cudaStreamDestroy(c->orb_stream);
   }
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < pislam_ctx::kGatherSlots; ++i)
     if (c->gathers[i].done) cudaEventDestroy(c->gathers[i].done);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->copy_in) cudaStreamDestroy(c->copy_in);
@@ -1012,6 +1047,8 @@ int pislam_b200_synchronize(pislam_ctx* c) {
   if (!c) return PISLAM_ERR_INVALID_ARG;
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaStreamSynchronize(c->comm_stream));
+  CK(cudaStreamSynchronize(c->copy_in));
+  CK(cudaStreamSynchronize(c->copy_out));
   if (c->d_p2p_timeout) {
     int t = 0;
     CK(cudaMemcpy(&t, c->d_p2p_timeout, 4, cudaMemcpyDeviceToHost));
@@ -1334,13 +1371,6 @@ size_t pislam_b200_record_kp_offset(int cap, int words) { return RecordLayout::m
 size_t pislam_b200_record_desc_offset(int cap, int words) { return RecordLayout::make(cap, words).desc_off; }
 size_t pislam_b200_record_level_offset(int cap, int words) { return RecordLayout::make(cap, words).level_off; }
 
-int pislam_b200_extract_batch_async(pislam_ctx* c, const uint8_t* d_stacks, size_t frame_stride, int nframes,
-                                    const pislam_pyramid_desc* d, int cap, void* d_records) {
-  if (!c) return PISLAM_ERR_INVALID_ARG;
-  CKS(set_device(c));
-  return enqueue_extract(c, d_stacks, frame_stride, nframes, d, cap, static_cast<uint8_t*>(d_records));
-}
-
 namespace {
 // What a fused call starts from: stacked pyramids (the reference's input, README.md:56-83) or base frames that the
 // pyramid builder expands on the device first.  Host or device memory.
@@ -1354,8 +1384,13 @@ struct FrameSource {
 
 // The whole fused path for a batch, blocking.  Host sources are pipelined in chunks over three streams:
 // copy_in (H2D of chunk i+1) || stream (kernels of chunk i) || copy_out (D2H of the records of chunk i-1).
-int extract_pipeline(pislam_ctx* c, const FrameSource& src, int nframes, const pislam_pyramid_desc* d, int cap,
-                     void* records) {
+// Enqueues the whole fused path for a batch; nothing here waits for the device.  Host sources are pipelined in
+// chunks over three streams: copy_in (H2D of chunk i+1) || stream (kernels of chunk i) || copy_out (D2H of the
+// records of chunk i-1).  The device staging (stacks / base frames / records of host destinations) is double-buffered
+// per call, so a caller that issues calls back to back (pislam_b200_extract_*_async) keeps the copy engine busy
+// across calls: the H2D of call k+1 runs under the kernels and the D2H of call k.
+int pipeline_enqueue(pislam_ctx* c, const FrameSource& src, int nframes, const pislam_pyramid_desc* d, int cap,
+                     void* records, uint8_t** d_records_out, bool* rec_on_host_out) {
   if (!c || !src.p || !records || nframes < 1) return PISLAM_ERR_INVALID_ARG;
   CKS(set_device(c));
   CKS(validate_desc(d, cap, true));
@@ -1368,15 +1403,26 @@ int extract_pipeline(pislam_ctx* c, const FrameSource& src, int nframes, const p
   const size_t rec_bytes = RecordLayout::make(cap, d->words).bytes;
   const bool src_on_host = !is_device_ptr(src.p);
   const bool rec_on_host = !is_device_ptr(records);
+  *rec_on_host_out = rec_on_host;
+  // staging set of this call; the other set may still be in use by the previous call's kernels and copies
+  const int b = c->stage_turn;
+  c->stage_turn ^= 1;
+  pislam_ctx::Staging& S = c->staging[b];
+  CK(cudaStreamWaitEvent(c->stream, S.rec_free, 0));   // the D2H of the call before last has left S.records
+  CK(cudaStreamWaitEvent(c->copy_in, S.src_free, 0));  // ... and its kernels have read S.stacks / S.bases
   uint8_t* d_records = static_cast<uint8_t*>(records);
   if (rec_on_host) {
-    CK(c->records.reserve(rec_bytes * nframes, false, c->stream));
-    d_records = c->records.as<uint8_t>();
+    CK(S.records.reserve_any(rec_bytes * nframes));
+    d_records = S.records.as<uint8_t>();
   }
+  *d_records_out = d_records;
   if (!src.base && !src_on_host) {
     CKS(enqueue_extract(c, src.p, stack_stride, nframes, d, cap, d_records));
-    if (rec_on_host) CK(cudaMemcpyAsync(records, d_records, rec_bytes * nframes, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    if (rec_on_host) {
+      CK(cudaEventRecord(c->ev_k[0], c->stream));
+      CK(cudaStreamWaitEvent(c->copy_out, c->ev_k[0], 0));
+      CK(cudaMemcpyAsync(records, d_records, rec_bytes * nframes, cudaMemcpyDeviceToHost, c->copy_out));
+    }
   } else {
     // chunks: a host source is cut for the copy/compute overlap; device-resident base frames are cut so that a
     // chunk's freshly built stacks are still in L2 when the detector and the descriptor kernel read them
@@ -1402,29 +1448,26 @@ int extract_pipeline(pislam_ctx* c, const FrameSource& src, int nframes, const p
     if (src.base) {
       // the stacks of ALL chunks stay allocated (the descriptor kernel of a chunk may still run while the next
       // chunk's pyramid is being built); padding columns are never read by the detector, so they are not cleared
-      CK(c->stacks.reserve(frame_bytes * nframes, false, c->stream));
-      d_stacks = c->stacks.as<uint8_t>();
+      CK(S.stacks.reserve_any(frame_bytes * nframes));
+      d_stacks = S.stacks.as<uint8_t>();
       if (src_on_host) {
         bp = (d->widths[0] + 15) & ~15;
         bstride = (size_t)bp * d->heights[0];
-        CK(c->bases.reserve(bstride * nframes, false, c->stream));
-        d_bases = c->bases.as<uint8_t>();
+        CK(S.bases.reserve_any(bstride * nframes));
+        d_bases = S.bases.as<uint8_t>();
       }
     } else {
       const size_t total = (size_t)(nframes - 1) * stack_stride + frame_bytes;
-      CK(c->stacks.reserve(total, false, c->stream));
-      d_stacks = c->stacks.as<uint8_t>();
+      CK(S.stacks.reserve_any(total));
+      d_stacks = S.stacks.as<uint8_t>();
     }
-    // earlier work on the ctx stream may still read the staging buffers
-    CK(cudaEventRecord(c->ev_k[0], c->stream));
-    CK(cudaStreamWaitEvent(c->copy_in, c->ev_k[0], 0));
     int i = 0;
     for (int f0 = 0; f0 < nframes; f0 += per, ++i) {
       const int nf = std::min(per, nframes - f0);
       const int e = i % pislam_ctx::kMaxChunks;
       if (src_on_host) {
         if (src.base)
-          CKS(copy_bases_h2d(c->copy_in, src.p, src.pitch, src.stride, c->bases.as<uint8_t>(), bp, d->widths[0],
+          CKS(copy_bases_h2d(c->copy_in, src.p, src.pitch, src.stride, S.bases.as<uint8_t>(), bp, d->widths[0],
                              d->heights[0], f0, nf));
         else
           CKS(copy_frames_h2d(c, c->copy_in, src.p, d_stacks, stack_stride, frame_bytes, f0, nf, d));
@@ -1443,9 +1486,22 @@ int extract_pipeline(pislam_ctx* c, const FrameSource& src, int nframes, const p
                            rec_bytes * nf, cudaMemcpyDeviceToHost, c->copy_out));
       }
     }
-    CK(cudaStreamSynchronize(c->stream));
-    if (rec_on_host) CK(cudaStreamSynchronize(c->copy_out));
   }
+  // the staging set is free again once this call's kernels have run and its records have left the device
+  CK(cudaEventRecord(S.src_free, c->stream));
+  CK(cudaEventRecord(S.rec_free, rec_on_host ? c->copy_out : c->stream));
+  return PISLAM_OK;
+}
+
+// The blocking form: enqueue, wait, report capacity overflow
+int extract_pipeline(pislam_ctx* c, const FrameSource& src, int nframes, const pislam_pyramid_desc* d, int cap,
+                     void* records) {
+  uint8_t* d_records = nullptr;
+  bool rec_on_host = false;
+  CKS(pipeline_enqueue(c, src, nframes, d, cap, records, &d_records, &rec_on_host));
+  CK(cudaStreamSynchronize(c->stream));
+  if (rec_on_host) CK(cudaStreamSynchronize(c->copy_out));
+  const size_t rec_bytes = RecordLayout::make(cap, d->words).bytes;
   if (rec_on_host) {
     const uint8_t* r = static_cast<const uint8_t*>(records);
     for (int f = 0; f < nframes; ++f) {
@@ -1457,6 +1513,27 @@ int extract_pipeline(pislam_ctx* c, const FrameSource& src, int nframes, const p
   return check_capacity(c, d_records, nframes, rec_bytes);
 }
 }  // namespace
+
+int pislam_b200_extract_batch_async(pislam_ctx* c, const uint8_t* stacks, size_t frame_stride, int nframes,
+                                    const pislam_pyramid_desc* d, int cap, void* records) {
+  if (!c) return PISLAM_ERR_INVALID_ARG;
+  CKS(set_device(c));
+  if (stacks && records && is_device_ptr(stacks) && is_device_ptr(records))
+    return enqueue_extract(c, stacks, frame_stride, nframes, d, cap, static_cast<uint8_t*>(records));
+  const FrameSource src = {stacks, false, 0, frame_stride, 0};
+  uint8_t* d_records = nullptr;
+  bool rec_on_host = false;
+  return pipeline_enqueue(c, src, nframes, d, cap, records, &d_records, &rec_on_host);
+}
+
+int pislam_b200_extract_frames_async(pislam_ctx* c, const uint8_t* frames, int frame_pitch, size_t frame_stride,
+                                     int nframes, int blur, const pislam_pyramid_desc* d, int cap, void* records) {
+  if (!c) return PISLAM_ERR_INVALID_ARG;
+  const FrameSource src = {frames, true, frame_pitch, frame_stride, blur};
+  uint8_t* d_records = nullptr;
+  bool rec_on_host = false;
+  return pipeline_enqueue(c, src, nframes, d, cap, records, &d_records, &rec_on_host);
+}
 
 int pislam_b200_extract_batch(pislam_ctx* c, const uint8_t* stacks, size_t frame_stride, int nframes,
                               const pislam_pyramid_desc* d, int cap, void* records) {
@@ -1671,14 +1748,15 @@ int pislam_b200_extract_allgather(pislam_ctx* c, const uint8_t* d_stacks, size_t
   // alternating buffers the previous gather (other buffer) keeps running under this batch's kernels
   pislam_ctx::GatherSlot& g = c->gathers[c->gather_turn];
   bool known = false;
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < pislam_ctx::kGatherSlots; ++i)
     if (c->gathers[i].ptr == d_all_records) {
       CK(cudaStreamWaitEvent(c->stream, c->gathers[i].done, 0));
       known = true;
     }
-  // a third buffer evicts the older entry: from then on nothing remembers that entry's gather, so order this
-  // call (and through the stream everything later) behind it
-  if (!known && g.ptr) CK(cudaStreamWaitEvent(c->stream, g.done, 0));
+  // a buffer beyond the tracked ones evicts the oldest entry: from then on nothing remembers that entry's gather, so
+  // order this call (and through the stream everything later) behind it
+  if (g.ptr && g.ptr != d_all_records) CK(cudaStreamWaitEvent(c->stream, g.done, 0));
+  (void)known;
   P2pPeers peers;
   memset(&peers, 0, sizeof(peers));
   uint32_t epoch = 0;
@@ -1703,7 +1781,9 @@ int pislam_b200_extract_allgather(pislam_ctx* c, const uint8_t* d_stacks, size_t
   cudaError_t e = cudaEventRecord(c->ev_extract, c->stream);
   if (e == cudaSuccess) e = cudaStreamWaitEvent(c->comm_stream, c->ev_extract, 0);
   if (e != cudaSuccess && st == PISLAM_OK) st = -(int)e;
-  if (win >= 0) {
+  static const bool no_exchange = getenv("PISLAM_B200_DEBUG_NO_EXCHANGE") != nullptr;  // timing experiments only
+  if (no_exchange) {
+  } else if (win >= 0) {
     P2pPushParams Q;
     memset(&Q, 0, sizeof(Q));
     Q.peers = peers;
@@ -1725,7 +1805,7 @@ int pislam_b200_extract_allgather(pislam_ctx* c, const uint8_t* d_stacks, size_t
     const int r = g_nccl.AllGather(mine, d_all_records, slot, /*ncclInt8*/ 0, c->comm, c->comm_stream);
     if (r != 0) return PISLAM_ERR_NCCL - r;
   }
-  c->gather_turn ^= 1;
+  c->gather_turn = (c->gather_turn + 1) % pislam_ctx::kGatherSlots;
   g.ptr = d_all_records;
   CK(cudaEventRecord(g.done, c->comm_stream));
   return st;
@@ -1734,8 +1814,10 @@ int pislam_b200_extract_allgather(pislam_ctx* c, const uint8_t* d_stacks, size_t
 int pislam_b200_join(pislam_ctx* c) {
   if (!c) return PISLAM_ERR_INVALID_ARG;
   CKS(set_device(c));
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < pislam_ctx::kGatherSlots; ++i)
     if (c->gathers[i].ptr) CK(cudaStreamWaitEvent(c->stream, c->gathers[i].done, 0));
+  // ... and for the record copies of the issue-only host pipelines (pislam_b200_extract_*_async)
+  for (int i = 0; i < 2; ++i) CK(cudaStreamWaitEvent(c->stream, c->staging[i].rec_free, 0));
   return PISLAM_OK;
 }
 

@@ -424,6 +424,42 @@ def test_literal_keypoints_outside_image_rejected(ctx):
         ctx.extract_pyramid(np.zeros((100, 640), np.uint8), api.make_desc(VGA), cap=64)
 
 
+def test_async_host_pipeline_back_to_back(ctx, oracle):
+    """pislam_b200_extract_batch_async / _extract_frames_async on host buffers: several calls issued back to back
+    (double-buffered device staging: the copies of call k+1 overlap the kernels of call k) into separate record
+    buffers, one synchronize at the end; every call's records equal the blocking call's and the oracle's."""
+    import torch
+    from pislam_b200.pyramid import build_stack, synthetic_base
+    lay = pyramid_layout(320, 240, nlevels=4)
+    d = api.make_desc(lay, log_bucket=4, bucket_limit=3)
+    cap, nf, ncalls = 1024, 9, 5
+    rec_bytes = api.record_layout(cap, 8)["bytes"]
+    bases = [[synthetic_base(320, 240, 0x5EED0000 + 900 + 10 * k + f) for f in range(nf)] for k in range(ncalls)]
+    h_bases = [torch.from_numpy(np.stack(b)).pin_memory() for b in bases]
+    h_stacks = [torch.from_numpy(np.stack([build_stack(x, lay) for x in b])).pin_memory() for b in bases]
+    for kind in ("stacks", "bases"):
+        outs = [torch.zeros(nf * rec_bytes, dtype=torch.uint8).pin_memory() for _ in range(ncalls)]
+        for k in range(ncalls):
+            if kind == "stacks":
+                st = ctx.extract_batch_ptr(h_stacks[k].data_ptr(), lay.stack_bytes, nf, d, cap, outs[k].data_ptr(),
+                                           asynchronous=True)
+            else:
+                st = ctx.extract_frames_ptr(h_bases[k].data_ptr(), 320, 320 * 240, nf, d, cap, outs[k].data_ptr(),
+                                            asynchronous=True)
+            assert st == 0
+        ctx.synchronize()
+        for k in range(ncalls):
+            recs = api.parse_records(outs[k].numpy(), nf, cap, 8)
+            for f in (0, nf // 2, nf - 1):
+                okp, olv, odesc = oracle_pyramid(oracle, h_stacks[k].numpy()[f], lay, log_bucket=4, bucket_limit=3)
+                assert_same(recs[f][0], okp, "%s call %d frame %d keypoints" % (kind, k, f))
+                assert_same(recs[f][2], odesc, "%s call %d frame %d descriptors" % (kind, k, f))
+            blocking = ctx.extract_batch(h_stacks[k].numpy(), d, cap=cap)
+            for f in range(nf):
+                assert_same(recs[f][0], blocking[f][0], "%s call %d frame %d vs blocking" % (kind, k, f))
+                assert_same(recs[f][2], blocking[f][2], "%s call %d frame %d descriptors vs blocking" % (kind, k, f))
+
+
 def test_argument_errors(ctx):
     stack = np.zeros((VGA.rows, VGA.vstep), np.uint8)
     with pytest.raises(api.PislamError) as e:
