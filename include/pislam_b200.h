@@ -62,11 +62,12 @@ int pislam_b200_set_tma(pislam_ctx* ctx, int enable);
 int pislam_b200_set_sub_batch(pislam_ctx* ctx, int frames);
 /* Per-kernel timing of the fused path (bench.py's roofline): while enabled, CUDA events are recorded on
  * the ctx stream around every launch of [0] front_tile_kernel, [1] order_kernel, [2] orb_kernel,
- * [3] pyramid_build_kernel.
+ * [3] pyramid_build_kernel, [4] the record exchange of pislam_b200_extract_allgather (on its own stream: from the
+ * moment the records are ready to the moment every peer's records have arrived).
  * pislam_b200_kernel_times synchronises, returns the summed durations (ms) and launch counts since the
  * last call, and clears them. */
 int pislam_b200_set_profiling(pislam_ctx* ctx, int enable);
-int pislam_b200_kernel_times(pislam_ctx* ctx, double ms[4], long count[4]);
+int pislam_b200_kernel_times(pislam_ctx* ctx, double ms[5], long count[5]);
 
 /* ---- literal stages (host buffers) ---------------------------------------------------------- */
 /* pislam::fastDetect<vstep,border>(width,height,img,out,threshold)        reference Fast.h:54-158 */
@@ -221,6 +222,8 @@ int pislam_b200_extract_allgather(pislam_ctx* ctx, const uint8_t* d_stacks, size
  * peer mapping is not possible (no IPC, more than 16 ranks, more than 8 buffers): the buffer then keeps working
  * through ncclAllGather.  Registrations live until pislam_b200_comm_destroy. */
 int pislam_b200_comm_register(pislam_ctx* ctx, void* d_buf, size_t bytes);
+/* CTAs of the exchange's copy kernel (default 32: it runs under the next batch's detector and should leave it the SMs). */
+int pislam_b200_set_exchange_ctas(pislam_ctx* ctx, int ctas);
 /* Number of buffers registered for the size-aware exchange (0: every gather goes through ncclAllGather). */
 int pislam_b200_comm_p2p_enabled(pislam_ctx* ctx);
 

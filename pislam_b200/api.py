@@ -94,6 +94,7 @@ _SIGNATURES = {
     "pislam_b200_comm_destroy": (C.c_int, [C.c_void_p]),
     "pislam_b200_comm_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "pislam_b200_comm_p2p_enabled": (C.c_int, [C.c_void_p]),
+    "pislam_b200_set_exchange_ctas": (C.c_int, [C.c_void_p, C.c_int]),
     "pislam_b200_extract_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                                                 C.POINTER(PyramidDesc), C.c_int, C.c_void_p]),
     "pislam_b200_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -233,10 +234,10 @@ class Context:
         self._ok(self.lib.pislam_b200_set_profiling(self._h, int(bool(enable))))
 
     def kernel_times(self):
-        """(ms[4], count[4]) for front_tile_kernel, order_kernel, orb_kernel, pyramid_build_kernel since the
-        last call."""
-        ms = (C.c_double * 4)()
-        cnt = (C.c_long * 4)()
+        """(ms[5], count[5]) for front_tile_kernel, order_kernel, orb_kernel, pyramid_build_kernel and the record
+        exchange since the last call."""
+        ms = (C.c_double * 5)()
+        cnt = (C.c_long * 5)()
         self._ok(self.lib.pislam_b200_kernel_times(self._h, ms, cnt))
         return list(ms), list(cnt)
 
@@ -456,6 +457,9 @@ class Context:
             return False
         self._ok(st)
         return True
+
+    def set_exchange_ctas(self, ctas):
+        self._ok(self.lib.pislam_b200_set_exchange_ctas(self._h, int(ctas)))
 
     @property
     def p2p_windows(self):

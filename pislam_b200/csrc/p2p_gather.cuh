@@ -4,14 +4,15 @@
 // one batch per GPU and the per-frame records meet on every GPU.  ncclAllGather has to move the fixed-capacity
 // records (2048 slots per frame, ~850 used); this exchange moves only what is live:
 //
-//   p2p_push_kernel   grid (slots per rank, peers): copies header + n keypoints + n descriptors + n level bytes of
-//                     one local record straight into the same slot of one peer's gather buffer (16-byte stores over
-//                     the peer mapping of a buffer registered with pislam_b200_comm_register)
+//   p2p_push_kernel   a few dozen persistent CTAs loop over (record, peer) pairs: header + n keypoints + n descriptors
+//                     + n level bytes of a local record go straight into the same slot of the peer's gather buffer
+//                     (16-byte stores over the peer mapping of a buffer registered with pislam_b200_comm_register)
 //   p2p_flag_kernel   one thread per peer: publishes an epoch in the peer's flag block (system-scope release)
 //   p2p_wait_kernel   one thread per peer: waits for that peer's epoch in the local flag block (bounded spin)
 //
 // Protocol per call and registered buffer (epoch e, identical on every rank because the calls are collective):
-//   ctx stream :  flag READY(e) to every peer  ->  detector / descriptor kernels write the local slot
+//   flag stream:  (after everything enqueued on the ctx stream so far)  flag READY(e) to every peer
+//   ctx stream :  detector / descriptor kernels write the local slot
 //   comm stream:  wait READY(e) from every peer (their buffer may be overwritten)  ->  push  ->  flag DONE(e)
 //                 ->  wait DONE(e) from every peer (their pushes have landed here)
 // No kernel spins while holding more than one CTA, and a peer that never arrives trips a ~10 s timeout that is
@@ -87,20 +88,29 @@ __device__ __forceinline__ void p2p_copy(uint8_t* dst, const uint8_t* src, unsig
   }
 }
 
+// A small persistent grid: the exchange runs on its own stream UNDER the next batch's detector, whose grid wants
+// every CTA slot; one CTA per (record, peer) pair (1792 CTAs of 256 threads for 256 records and 7 peers) takes all of
+// them for ~80 us and costs the step exactly that (profiles/r02_probe_8gpu_exchange.txt: 0.498 ms per step against
+// 0.419 without any exchange).  A few dozen CTAs that loop over the pairs keep enough 16-byte stores in flight for
+// the NVLink rate the exchange needs (56 MB in one step time) and leave the SMs to the detector.
 __global__ void __launch_bounds__(256) p2p_push_kernel(const __grid_constant__ P2pPushParams P) {
-  const int slot = blockIdx.x;
-  const int peer = (P.rank + 1 + blockIdx.y) % P.nranks;
-  const unsigned long long off = P.slot_offset + (unsigned long long)slot * P.rec.bytes;
-  const uint8_t* src = P.peers.buf[P.rank] + off;
-  uint8_t* dst = P.peers.buf[peer] + off;
-  const uint32_t n = min(*reinterpret_cast<const uint32_t*>(src), (uint32_t)P.cap);
+  const int npairs = P.slots_per_rank * (P.nranks - 1);
   // every field starts on a 16-byte boundary when cap is a multiple of 4 (kp 4*cap bytes, descriptors 4*cap*words)
   const bool vec16 = (P.cap & 3) == 0;
-  p2p_copy(dst, src, REC_HEADER_WORDS * 4, true);
-  if (n == 0) return;
-  p2p_copy(dst + P.rec.kp_off, src + P.rec.kp_off, 4u * n, vec16);
-  if (P.words > 0) p2p_copy(dst + P.rec.desc_off, src + P.rec.desc_off, 4u * n * (unsigned)P.words, vec16);
-  p2p_copy(dst + P.rec.level_off, src + P.rec.level_off, n, vec16);
+  for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    // consecutive CTAs serve different peers, so every NVLink port is busy from the start
+    const int pi = pair % (P.nranks - 1), slot = pair / (P.nranks - 1);
+    const int peer = (P.rank + 1 + pi) % P.nranks;
+    const unsigned long long off = P.slot_offset + (unsigned long long)slot * P.rec.bytes;
+    const uint8_t* src = P.peers.buf[P.rank] + off;
+    uint8_t* dst = P.peers.buf[peer] + off;
+    const uint32_t n = min(*reinterpret_cast<const uint32_t*>(src), (uint32_t)P.cap);
+    p2p_copy(dst, src, REC_HEADER_WORDS * 4, true);
+    if (n == 0) continue;
+    p2p_copy(dst + P.rec.kp_off, src + P.rec.kp_off, 4u * n, vec16);
+    if (P.words > 0) p2p_copy(dst + P.rec.desc_off, src + P.rec.desc_off, 4u * n * (unsigned)P.words, vec16);
+    p2p_copy(dst + P.rec.level_off, src + P.rec.level_off, n, vec16);
+  }
 }
 
 }  // namespace pb

@@ -215,8 +215,8 @@ struct pislam_ctx {
   cudaEvent_t ev_extract = nullptr;
   // sub-batches: the descriptor kernel of sub-batch k runs on its own (high-priority) stream under the detector of
   // sub-batch k+1, while the sub-batch's stacks are still in L2
-  cudaStream_t orb_stream = nullptr;
-  cudaEvent_t ev_sub = nullptr, ev_orb = nullptr;
+  cudaStream_t orb_stream = nullptr, flag_stream = nullptr;
+  cudaEvent_t ev_sub = nullptr, ev_orb = nullptr, ev_ready = nullptr;
   int sub_frames = 0;  // frames per sub-batch (0: the whole call in one piece)
   static const int kGatherSlots = 4;
   struct GatherSlot {
@@ -237,6 +237,7 @@ struct pislam_ctx {
     uint32_t epoch = 0;
   };
   bool p2p_ok = false;
+  int push_ctas = 32;  // CTAs of p2p_push_kernel (it runs under the next batch's detector: few CTAs, see p2p_gather.cuh)
   uint32_t* d_flags = nullptr;  // this rank's flag block (written by the peers)
   uint32_t* peer_flags[P2P_MAX_RANKS] = {};
   int* d_p2p_timeout = nullptr;
@@ -257,7 +258,7 @@ struct pislam_ctx {
   bool profiling = false;
   struct ProfSpan {
     cudaEvent_t a, b;
-    int which;  // 0 front_tile_kernel, 1 order_kernel, 2 orb_kernel, 3 pyramid_build_kernel
+    int which;  // 0 front_tile_kernel, 1 order_kernel, 2 orb_kernel, 3 pyramid_build_kernel, 4 record exchange
   };
   std::vector<ProfSpan> spans;
 };
@@ -697,7 +698,7 @@ int enqueue_pyramid(pislam_ctx* c, const uint8_t* d_frames, int frame_pitch, siz
   P.stack_stride = stack_stride;
   P.zero_padding = zero_padding ? 1 : 0;
   span_begin(c, 3);
-  pyramid_build_kernel<<<dim3(P.tile0[P.nlevels], nframes), dim3(32, PYR_TH), 0, c->stream>>>(P);
+  pyramid_build_kernel<<<dim3(P.tile0[P.nlevels], nframes), dim3(32, PYR_BLOCK_ROWS), 0, c->stream>>>(P);
   span_end(c);
   return check_launch(c);
 }
@@ -911,6 +912,8 @@ int pislam_b200_create(pislam_ctx** out, int device, size_t max_stack_bytes, int
       int prio_lo = 0, prio_hi = 0;
       if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) prio_hi = 0;
       if ((e = cudaStreamCreateWithPriority(&c->orb_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) { st = -(int)e; break; }
+      if ((e = cudaStreamCreateWithPriority(&c->flag_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) { st = -(int)e; break; }
+      if ((e = cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming)) != cudaSuccess) { st = -(int)e; break; }
     }
     for (int i = 0; i < 2 && st == PISLAM_OK; ++i) {
       if ((e = cudaEventCreateWithFlags(&c->staging[i].src_free, cudaEventDisableTiming)) != cudaSuccess) st = -(int)e;
@@ -1012,6 +1015,11 @@ int pislam_b200_destroy(pislam_ctx* c) {
   if (c->ev_extract) cudaEventDestroy(c->ev_extract);
   if (c->ev_sub) cudaEventDestroy(c->ev_sub);
   if (c->ev_orb) cudaEventDestroy(c->ev_orb);
+  if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+  if (c->flag_stream) {
+    cudaStreamSynchronize(c->flag_stream);
+    cudaStreamDestroy(c->flag_stream);
+  }
   if (c->orb_stream) {
     cudaStreamSynchronize(c->orb_stream);
     cudaStreamDestroy(c->orb_stream);
@@ -1049,6 +1057,7 @@ int pislam_b200_synchronize(pislam_ctx* c) {
   CK(cudaStreamSynchronize(c->comm_stream));
   CK(cudaStreamSynchronize(c->copy_in));
   CK(cudaStreamSynchronize(c->copy_out));
+  CK(cudaStreamSynchronize(c->flag_stream));
   if (c->d_p2p_timeout) {
     int t = 0;
     CK(cudaMemcpy(&t, c->d_p2p_timeout, 4, cudaMemcpyDeviceToHost));
@@ -1078,11 +1087,12 @@ int pislam_b200_set_profiling(pislam_ctx* c, int enable) {
   return PISLAM_OK;
 }
 
-int pislam_b200_kernel_times(pislam_ctx* c, double ms[4], long count[4]) {
+int pislam_b200_kernel_times(pislam_ctx* c, double ms[5], long count[5]) {
   if (!c || !ms || !count) return PISLAM_ERR_INVALID_ARG;
   CKS(set_device(c));
   CK(cudaStreamSynchronize(c->stream));
-  for (int k = 0; k < 4; ++k) {
+  CK(cudaStreamSynchronize(c->comm_stream));
+  for (int k = 0; k < 5; ++k) {
     ms[k] = 0.0;
     count[k] = 0;
   }
@@ -1677,6 +1687,7 @@ int pislam_b200_comm_destroy(pislam_ctx* c) {
     CKS(set_device(c));
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->comm_stream);
+    cudaStreamSynchronize(c->flag_stream);
     p2p_teardown(c);
     g_nccl.CommDestroy(c->comm);
     c->comm = nullptr;
@@ -1718,6 +1729,12 @@ int pislam_b200_comm_register(pislam_ctx* c, void* d_buf, size_t bytes) {
   for (int r = 0; r < c->nranks; ++r) ok = ok && *reinterpret_cast<const int*>(all.data() + r * sizeof(int));
   if (!ok) return PISLAM_ERR_UNSUPPORTED;  // on every rank alike: the buffer keeps working through ncclAllGather
   c->windows.push_back(w);
+  return PISLAM_OK;
+}
+
+int pislam_b200_set_exchange_ctas(pislam_ctx* c, int ctas) {
+  if (!c || ctas < 1) return PISLAM_ERR_INVALID_ARG;
+  c->push_ctas = ctas;
   return PISLAM_OK;
 }
 
@@ -1767,8 +1784,12 @@ int pislam_b200_extract_allgather(pislam_ctx* c, const uint8_t* d_stacks, size_t
       peers.buf[r] = w.peer[r] + (all - w.local);
       peers.flags[r] = c->peer_flags[r];
     }
-    // READY(e): from here on the peers may overwrite their slots of this rank's buffer
-    p2p_flag_kernel<<<1, 32, 0, c->stream>>>(peers, c->nranks, c->rank, win, P2P_READY, epoch);
+    // READY(e): from here on (everything enqueued on the ctx stream so far has run) the peers may overwrite their
+    // slots of this rank's buffer.  The flag goes out on its own stream: on the ctx stream it would sit between the
+    // descriptor kernel of one batch and the detector of the next
+    CK(cudaEventRecord(c->ev_ready, c->stream));
+    CK(cudaStreamWaitEvent(c->flag_stream, c->ev_ready, 0));
+    p2p_flag_kernel<<<1, 32, 0, c->flag_stream>>>(peers, c->nranks, c->rank, win, P2P_READY, epoch);
     CKS(check_launch(c));
   }
   int st = enqueue_extract(c, d_stacks, frame_stride, nframes_local, d, cap, mine);
@@ -1782,6 +1803,7 @@ int pislam_b200_extract_allgather(pislam_ctx* c, const uint8_t* d_stacks, size_t
   if (e == cudaSuccess) e = cudaStreamWaitEvent(c->comm_stream, c->ev_extract, 0);
   if (e != cudaSuccess && st == PISLAM_OK) st = -(int)e;
   static const bool no_exchange = getenv("PISLAM_B200_DEBUG_NO_EXCHANGE") != nullptr;  // timing experiments only
+  span_begin(c, 4, c->comm_stream);
   if (no_exchange) {
   } else if (win >= 0) {
     P2pPushParams Q;
@@ -1795,7 +1817,7 @@ int pislam_b200_extract_allgather(pislam_ctx* c, const uint8_t* d_stacks, size_t
     Q.words = d->words;
     Q.cap = cap;
     p2p_wait_kernel<<<1, 32, 0, c->comm_stream>>>(c->d_flags, c->nranks, c->rank, win, P2P_READY, epoch, c->d_p2p_timeout);
-    p2p_push_kernel<<<dim3(slots_per_rank, c->nranks - 1), 256, 0, c->comm_stream>>>(Q);
+    p2p_push_kernel<<<std::min(c->push_ctas, slots_per_rank * (c->nranks - 1)), 256, 0, c->comm_stream>>>(Q);
     p2p_flag_kernel<<<1, 32, 0, c->comm_stream>>>(peers, c->nranks, c->rank, win, P2P_DONE, epoch);
     p2p_wait_kernel<<<1, 32, 0, c->comm_stream>>>(c->d_flags, c->nranks, c->rank, win, P2P_DONE, epoch, c->d_p2p_timeout);
     c->launches += 3;
@@ -1805,6 +1827,7 @@ int pislam_b200_extract_allgather(pislam_ctx* c, const uint8_t* d_stacks, size_t
     const int r = g_nccl.AllGather(mine, d_all_records, slot, /*ncclInt8*/ 0, c->comm, c->comm_stream);
     if (r != 0) return PISLAM_ERR_NCCL - r;
   }
+  span_end(c, c->comm_stream);
   c->gather_turn = (c->gather_turn + 1) % pislam_ctx::kGatherSlots;
   g.ptr = d_all_records;
   CK(cudaEventRecord(g.done, c->comm_stream));

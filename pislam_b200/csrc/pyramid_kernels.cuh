@@ -110,10 +110,12 @@ __global__ void bilinear_blocks_kernel(const uint8_t* __restrict__ img, uint8_t*
 // NOT reference code -- the reference leaves the pyramid to its caller (README.md:28-31).  Definition
 // (oracle/pislam_oracle.h:po_resize_bilinear): every level is a pixel-centre-aligned bilinear resize of the base
 // frame, taps and 8-bit weights from per-level tables the host builds once per geometry.
-//   grid (tiles of 128 x 8 output pixels over all levels, nframes), block (32, 8): one thread = four adjacent
-//   output pixels = one 32-bit store; level 0 (identity) is a straight copy.
+//   grid (tiles of 128 x 32 output pixels over all levels, nframes), block (32, 8): one thread = four adjacent
+//   output pixels (one 32-bit store) in each of four rows, with the same horizontal taps; level 0 (identity) is a
+//   straight copy.
 // --------------------------------------------------------------------------------------------------
-constexpr int PYR_TW = 128, PYR_TH = 8, PYR_MAX_LEVELS = 16;
+constexpr int PYR_TW = 128, PYR_BLOCK_ROWS = 8, PYR_ROWS_PER_THREAD = 4, PYR_TH = PYR_BLOCK_ROWS * PYR_ROWS_PER_THREAD,
+              PYR_MAX_LEVELS = 16;
 
 struct PyramidParams {
   const uint8_t* base;  // frame 0
@@ -137,6 +139,8 @@ __host__ __device__ __forceinline__ uint32_t pack_tap(int i0, int i1, int f) {
 }
 
 __global__ void __launch_bounds__(256) pyramid_build_kernel(const __grid_constant__ PyramidParams P) {
+  // tile -> (level, tile row, tile column): a handful of uniform instructions per thread, amortised over the
+  // PYR_ROWS_PER_THREAD rows every thread produces (per 4 pixels they were 40 % of the kernel's instructions)
   int l = 0;
   const int t = blockIdx.x;
 #pragma unroll 1
@@ -144,56 +148,69 @@ __global__ void __launch_bounds__(256) pyramid_build_kernel(const __grid_constan
   const int tl = t - P.tile0[l];
   const int ty = tl / P.tiles_x[l], tx = tl - ty * P.tiles_x[l];
   const int w = P.w[l], h = P.h[l];
-  const int y = ty * PYR_TH + threadIdx.y;
   const int x = tx * PYR_TW + 4 * threadIdx.x;
-  if (y >= h) return;
-  uint8_t* orow = P.stacks + (size_t)blockIdx.y * P.stack_stride + (size_t)(P.row_off[l] + y) * P.vstep;
-  // four pixels at column xs of the output row (bytes past the pitch are dropped)
-  auto store4 = [&](int xs, uint32_t v) {
-    uint8_t* o = orow + xs;
-    if (xs + 4 <= P.vstep && (reinterpret_cast<uintptr_t>(o) & 3) == 0) *reinterpret_cast<uint32_t*>(o) = v;
-    else
-      for (int b = 0; b < 4 && xs + b < P.vstep; ++b) o[b] = (uint8_t)(v >> (8 * b));
-  };
-  // the last tile of a level row also clears the padding right of the level, up to the pitch
-  const bool pad = P.zero_padding && tx == P.tiles_x[l] - 1;
-  if (pad)
-    for (int xz = x + PYR_TW; xz < P.vstep; xz += PYR_TW) store4(xz, 0u);
-  if (x >= w) {
-    if (pad && x < P.vstep) store4(x, 0u);
-    return;
-  }
+  const bool identity = w == P.W && h == P.H;
+  const bool pad = P.zero_padding && tx == P.tiles_x[l] - 1;  // the last tile of a level row also clears the padding
   const uint8_t* src = P.base + (size_t)blockIdx.y * P.base_stride;
-  uint32_t v = 0;
-  if (w == P.W && h == P.H) {  // identity level
-    const uint8_t* p = src + (size_t)y * P.base_pitch + x;
-    if (x + 4 <= w && (reinterpret_cast<uintptr_t>(p) & 3) == 0) v = __ldg(reinterpret_cast<const uint32_t*>(p));
-    else
-      for (int b = 0; b < 4 && x + b < w; ++b) v |= (uint32_t)__ldg(p + b) << (8 * b);
-  } else {
-    const uint32_t ye = __ldg(P.ytaps + P.yt0[l] + y);
-    const int fy = (int)((ye >> 16) & 0xffu);
-    const uint8_t* r0 = src + (size_t)(ye & 0x7fffu) * P.base_pitch;
-    const uint8_t* r1 = r0 + ((ye >> 15) & 1u) * P.base_pitch;
-    // the table is padded to a multiple of 4 entries per level, so one 16-byte load fetches this thread's four taps
+  uint8_t* lvl = P.stacks + (size_t)blockIdx.y * P.stack_stride + (size_t)P.row_off[l] * P.vstep;
+  // this thread's four horizontal taps (the table is padded to a multiple of 4 entries per level)
+  int x0[4] = {0, 0, 0, 0}, dx[4] = {0, 0, 0, 0}, fx[4] = {0, 0, 0, 0};
+  if (!identity && x < w) {
     const uint4 xe4 = __ldg(reinterpret_cast<const uint4*>(P.xtaps + P.xt0[l] + x));
     const uint32_t xe[4] = {xe4.x, xe4.y, xe4.z, xe4.w};
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      const int x0 = (int)(xe[b] & 0x7fffu), dx = (int)((xe[b] >> 15) & 1u), fx = (int)((xe[b] >> 16) & 0xffu);
-      const int a00 = __ldg(r0 + x0), a01 = __ldg(r0 + x0 + dx), a10 = __ldg(r1 + x0), a11 = __ldg(r1 + x0 + dx);
-      const int top = (a00 << 8) + (a01 - a00) * fx;  // a00*(256-fx) + a01*fx
-      const int bot = (a10 << 8) + (a11 - a10) * fx;
-      const int o = ((top << 8) + (bot - top) * fy + (1 << 15)) >> 16;
-      v |= (uint32_t)o << (8 * b);
+      x0[b] = (int)(xe[b] & 0x7fffu);
+      dx[b] = (int)((xe[b] >> 15) & 1u);
+      fx[b] = (int)((xe[b] >> 16) & 0xffu);
     }
-    if (x + 4 > w) v &= 0xffffffffu >> (8 * (x + 4 - w));  // padded table entries: columns >= w stay zero
   }
-  if (x + 4 > w && !P.zero_padding) {  // do not touch the bytes right of the level
-    for (int b = 0; x + b < w; ++b) orow[x + b] = (uint8_t)(v >> (8 * b));
-    return;
+#pragma unroll 1
+  for (int k = 0; k < PYR_ROWS_PER_THREAD; ++k) {
+    const int y = ty * PYR_TH + threadIdx.y + k * PYR_BLOCK_ROWS;
+    if (y >= h) break;
+    uint8_t* orow = lvl + (size_t)y * P.vstep;
+    // four pixels at column xs of the output row (bytes past the pitch are dropped)
+    auto store4 = [&](int xs, uint32_t v) {
+      uint8_t* o = orow + xs;
+      if (xs + 4 <= P.vstep && (reinterpret_cast<uintptr_t>(o) & 3) == 0) *reinterpret_cast<uint32_t*>(o) = v;
+      else
+        for (int b = 0; b < 4 && xs + b < P.vstep; ++b) o[b] = (uint8_t)(v >> (8 * b));
+    };
+    if (pad)
+      for (int xz = x + PYR_TW; xz < P.vstep; xz += PYR_TW) store4(xz, 0u);
+    if (x >= w) {
+      if (pad && x < P.vstep) store4(x, 0u);
+      continue;
+    }
+    uint32_t v = 0;
+    if (identity) {
+      const uint8_t* p = src + (size_t)y * P.base_pitch + x;
+      if (x + 4 <= w && (reinterpret_cast<uintptr_t>(p) & 3) == 0) v = __ldg(reinterpret_cast<const uint32_t*>(p));
+      else
+        for (int b = 0; b < 4 && x + b < w; ++b) v |= (uint32_t)__ldg(p + b) << (8 * b);
+    } else {
+      const uint32_t ye = __ldg(P.ytaps + P.yt0[l] + y);
+      const int fy = (int)((ye >> 16) & 0xffu);
+      const uint8_t* r0 = src + (size_t)(ye & 0x7fffu) * P.base_pitch;
+      const uint8_t* r1 = r0 + ((ye >> 15) & 1u) * P.base_pitch;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int a00 = __ldg(r0 + x0[b]), a01 = __ldg(r0 + x0[b] + dx[b]), a10 = __ldg(r1 + x0[b]),
+                  a11 = __ldg(r1 + x0[b] + dx[b]);
+        const int top = (a00 << 8) + (a01 - a00) * fx[b];  // a00*(256-fx) + a01*fx
+        const int bot = (a10 << 8) + (a11 - a10) * fx[b];
+        const int o = ((top << 8) + (bot - top) * fy + (1 << 15)) >> 16;
+        v |= (uint32_t)o << (8 * b);
+      }
+      if (x + 4 > w) v &= 0xffffffffu >> (8 * (x + 4 - w));  // padded table entries: columns >= w stay zero
+    }
+    if (x + 4 > w && !P.zero_padding) {  // do not touch the bytes right of the level
+      for (int b = 0; x + b < w; ++b) orow[x + b] = (uint8_t)(v >> (8 * b));
+      continue;
+    }
+    store4(x, v);
   }
-  store4(x, v);
 }
 
 // batched forms of the two blur passes (blockIdx.z = frame)

@@ -32,6 +32,29 @@ with api.Context(0) as ctx:
             good = all(np.array_equal(res[j][0], okp) and np.array_equal(res[j][2], odesc) for j in range(i, 48, 6))
             ok &= good
             print("batch frame", i, "buckets", (lb, bl), "n", len(okp), "match", good)
+    # pyramid builder in front of the path (host base frames, chunked pipeline, blur on and off) and the issue-only form
+    from pislam_b200.pyramid import synthetic_base
+    bases = np.stack([synthetic_base(320, 240, 0x5EED0000 + 70 + i) for i in range(3)] * 8)
+    for blur in (False, True):
+        d = api.make_desc(lay, log_bucket=4, bucket_limit=3)
+        res = ctx.extract_frames(bases, d, cap=1 << 13, blur=blur)
+        for i in range(3):
+            st_ = o.build_pyramid(bases[i], lay, blur=blur)
+            okp, olv, odesc = o.extract_pyramid(st_, lay.widths, lay.heights, lay.row_offsets, log_bucket=4, bucket_limit=3,
+                                                cap=1 << 13)
+            good = all(np.array_equal(res[j][0], okp) and np.array_equal(res[j][2], odesc) for j in range(i, 24, 3))
+            good &= np.array_equal(ctx.build_pyramid(bases[i:i + 1], d, blur=blur)[0], st_)
+            ok &= good
+            print("base frame", i, "blur", blur, "n", len(okp), "match", good)
+    # keypoints only with border 5: plain-load staging with linear addressing and the pitch-overrun spill
+    nz = noise_stack(lay, 12)
+    d5 = api.make_desc(lay, border=5, fast_threshold=45, harris_threshold=1 << 12, words=0)
+    kp, lv, _ = ctx.extract_pyramid(nz, d5, cap=1 << 16)
+    okp, olv, _ = o.extract_pyramid(nz, lay.widths, lay.heights, lay.row_offsets, border=5, fast_threshold=45,
+                                    harris_threshold=1 << 12, words=0, cap=1 << 16)
+    good = np.array_equal(kp, okp)
+    ok &= good
+    print("border 5 noise n", len(okp), "match", good)
     img = np.ascontiguousarray(stack[:240])
     out = np.zeros_like(img)
     ctx.fastDetect(320, 240, img, out, 20)

@@ -52,7 +52,7 @@ def main():
     hdr = rows[hi]
     ia, iinst, ithr, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), \
         hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
-    iconf = hdr.index("L1 Wavefronts Shared Excessive")
+    iconf = hdr.index("L1 Wavefronts Shared Excessive") if "L1 Wavefronts Shared Excessive" in hdr else None  # no smem: absent
     table = line_table(ksub)
     base = None
     agg = {}
@@ -68,7 +68,7 @@ def main():
             base = addr
         key, sass = table.get(addr - base, (None, "?"))
         a = agg.setdefault(key, [0, 0, 0, 0])
-        vals = [int(float(r[iinst] or 0)), int(float(r[ithr] or 0)), int(float(r[isamp] or 0)), int(float(r[iconf] or 0))]
+        vals = [int(float(r[iinst] or 0)), int(float(r[ithr] or 0)), int(float(r[isamp] or 0)), int(float(r[iconf] or 0)) if iconf is not None else 0]
         for k in range(4):
             a[k] += vals[k]
         for k in range(3):
