@@ -356,32 +356,54 @@ def run_gpu_arm(args):
         if st != 0:
             raise RuntimeError("extract failed: %d" % st)
 
-    def e2e_tail(st):
-        """N > 1: the records extracted into this rank's slot are all-gathered over NVLink and the rank's own records
-        are read back to the host"""
+    d2h_stream = torch.cuda.Stream() if world > 1 else None
+
+    def e2e_multi(call):
+        """N > 1: HOST frames in; the records are extracted into this rank's slot of a (registered) gather buffer through
+        the library's chunked pipeline, exchanged over NVLink on the library's second stream, and the rank's own
+        records are read back to the host on a third stream -- nothing in the step blocks, consecutive steps overlap"""
+        buf = d_alls[turn[0]]
+        turn[0] = (turn[0] + 1) % len(d_alls)
+        st = call(buf.data_ptr())
         if st not in (0, api.PISLAM_ERR_CAPACITY):
             raise RuntimeError("extract failed: %d" % st)
-        if world > 1:
-            g = ctx.allgather_ptr(d_all.data_ptr(), F * rec_bytes)
-            if g != 0:
-                raise RuntimeError("allgather failed: %d" % g)
-            with torch.cuda.stream(stream):
-                h_records.copy_(d_records, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(stream)  # this rank's records are complete here (the exchange runs on the library's second stream)
+        d2h_stream.wait_event(ev)
+        with torch.cuda.stream(d2h_stream):
+            h_records.copy_(buf[rank * F * rec_bytes:(rank + 1) * F * rec_bytes], non_blocking=True)
+
+    def e2e_single(st):
+        if st not in (0, api.PISLAM_ERR_CAPACITY):
+            raise RuntimeError("extract failed: %d" % st)
 
     def step_e2e(asynchronous=True):
         """the call a user makes: HOST stacks in, HOST records out (H2D + kernels + D2H inside the call).  The
         issue-only form (pislam_b200_extract_batch_async on pinned host buffers) lets consecutive calls overlap: the
         H2D of step k+1 runs under the kernels and the D2H of step k; the timed region ends after the last D2H."""
-        dst = h_records.data_ptr() if world == 1 else d_records.data_ptr()
-        e2e_tail(ctx.extract_batch_ptr(h_stacks.data_ptr(), frame_bytes, F, desc, CAP, dst, asynchronous=asynchronous))
+        if world == 1:
+            e2e_single(ctx.extract_batch_ptr(h_stacks.data_ptr(), frame_bytes, F, desc, CAP, h_records.data_ptr(),
+                                             asynchronous=asynchronous))
+        else:
+            e2e_multi(lambda all_ptr: ctx.extract_allgather_ptr(h_stacks.data_ptr(), frame_bytes, F, desc, CAP, all_ptr))
+            if not asynchronous:
+                ctx.synchronize()
+                d2h_stream.synchronize()
 
     def step_e2e_blocking():
         step_e2e(False)
 
     def step_e2e_base(asynchronous=True):
         """HOST base frames in, HOST records out: the pyramid is built on the GPU"""
-        dst = h_records.data_ptr() if world == 1 else d_records.data_ptr()
-        e2e_tail(ctx.extract_frames_ptr(h_bases.data_ptr(), W, W * H, F, desc, CAP, dst, asynchronous=asynchronous))
+        if world == 1:
+            e2e_single(ctx.extract_frames_ptr(h_bases.data_ptr(), W, W * H, F, desc, CAP, h_records.data_ptr(),
+                                              asynchronous=asynchronous))
+        else:
+            e2e_multi(lambda all_ptr: ctx.extract_frames_allgather_ptr(h_bases.data_ptr(), W, W * H, F, desc, CAP,
+                                                                       all_ptr))
+            if not asynchronous:
+                ctx.synchronize()
+                d2h_stream.synchronize()
 
     def step_e2e_base_blocking():
         step_e2e_base(False)
@@ -401,7 +423,9 @@ def run_gpu_arm(args):
         e0.record(stream)
         for _ in range(steps):
             fn()
-        ctx.join()  # the last all-gather (second stream) belongs to the timed region
+        ctx.join()  # the last exchange (second stream) and record copies belong to the timed region
+        if d2h_stream is not None:
+            stream.wait_stream(d2h_stream)
         e1.record(stream)
         barrier()
         t1 = time.perf_counter()

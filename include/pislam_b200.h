@@ -207,9 +207,15 @@ int pislam_b200_comm_destroy(pislam_ctx* ctx);
  * The gather is issued on a second stream behind the kernels, so with two alternating gather
  * buffers it overlaps the next batch's kernels; a buffer is never rewritten before its previous
  * gather has finished.  Enqueue only: pislam_b200_synchronize waits for kernels and gathers. */
-int pislam_b200_extract_allgather(pislam_ctx* ctx, const uint8_t* d_stacks, size_t frame_stride,
+int pislam_b200_extract_allgather(pislam_ctx* ctx, const uint8_t* stacks, size_t frame_stride,
                                   int nframes_local, int slots_per_rank, const pislam_pyramid_desc* desc,
                                   int cap, void* d_all_records);
+/* `stacks` may also be HOST memory (pinned): the rank's frames then go through the chunked H2D | kernels pipeline
+ * of pislam_b200_extract_batch_async straight into its slot, and the exchange follows on the second stream.
+ * The same from BASE frames (host or device; see pislam_b200_extract_frames): */
+int pislam_b200_extract_frames_allgather(pislam_ctx* ctx, const uint8_t* frames, int frame_pitch, size_t frame_stride,
+                                         int nframes_local, int blur, int slots_per_rank,
+                                         const pislam_pyramid_desc* desc, int cap, void* d_all_records);
 
 /* Registers a device buffer for the SIZE-AWARE record exchange (collective: every rank calls it, in the same
  * order, with a buffer of the same size; 16-byte aligned).  The buffer's allocation is mapped into every peer

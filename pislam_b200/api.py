@@ -97,6 +97,8 @@ _SIGNATURES = {
     "pislam_b200_set_exchange_ctas": (C.c_int, [C.c_void_p, C.c_int]),
     "pislam_b200_extract_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                                                 C.POINTER(PyramidDesc), C.c_int, C.c_void_p]),
+    "pislam_b200_extract_frames_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_int,
+                                                       C.c_int, C.POINTER(PyramidDesc), C.c_int, C.c_void_p]),
     "pislam_b200_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "pislam_b200_join": (C.c_int, [C.c_void_p]),
     "pislam_b200_match_hamming": (C.c_int, [C.c_void_p, _u32p, _u32p, _u8p, C.c_int, _u32p, _u32p, _u8p, C.c_int,
@@ -481,6 +483,17 @@ class Context:
         slots = nframes_local if slots_per_rank is None else slots_per_rank
         return self.lib.pislam_b200_extract_allgather(self._h, stacks_ptr, frame_stride, nframes_local, slots,
                                                       C.byref(desc), cap, all_records_ptr)
+
+
+def _frames_allgather(self, frames_ptr, frame_pitch, frame_stride, nframes_local, desc, cap, all_records_ptr,
+                      slots_per_rank=None, blur=False):
+    """pislam_b200_extract_frames_allgather: this rank's BASE frames (host or device) -> its slot, then the exchange."""
+    slots = nframes_local if slots_per_rank is None else slots_per_rank
+    return self.lib.pislam_b200_extract_frames_allgather(self._h, frames_ptr, frame_pitch, frame_stride, nframes_local,
+                                                         int(bool(blur)), slots, C.byref(desc), cap, all_records_ptr)
+
+
+Context.extract_frames_allgather_ptr = _frames_allgather
 
 
 def comm_unique_id():

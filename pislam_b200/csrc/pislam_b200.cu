@@ -1740,8 +1740,11 @@ int pislam_b200_set_exchange_ctas(pislam_ctx* c, int ctas) {
 
 int pislam_b200_comm_p2p_enabled(pislam_ctx* c) { return (c && c->p2p_ok) ? (int)c->windows.size() : 0; }
 
-int pislam_b200_extract_allgather(pislam_ctx* c, const uint8_t* d_stacks, size_t frame_stride, int nframes_local,
-                                  int slots_per_rank, const pislam_pyramid_desc* d, int cap, void* d_all_records) {
+namespace {
+int extract_allgather_impl(pislam_ctx* c, const FrameSource& src, int nframes_local, int slots_per_rank,
+                           const pislam_pyramid_desc* d, int cap, void* d_all_records) {
+  const uint8_t* d_stacks = src.p;
+  const size_t frame_stride = src.stride;
   if (!c || !d_all_records || !d || slots_per_rank < 1 || nframes_local < 0 || nframes_local > slots_per_rank ||
       (nframes_local > 0 && !d_stacks))
     return PISLAM_ERR_INVALID_ARG;
@@ -1792,7 +1795,16 @@ int pislam_b200_extract_allgather(pislam_ctx* c, const uint8_t* d_stacks, size_t
     p2p_flag_kernel<<<1, 32, 0, c->flag_stream>>>(peers, c->nranks, c->rank, win, P2P_READY, epoch);
     CKS(check_launch(c));
   }
-  int st = enqueue_extract(c, d_stacks, frame_stride, nframes_local, d, cap, mine);
+  int st = PISLAM_OK;
+  if (nframes_local > 0 && (src.base || !is_device_ptr(d_stacks))) {
+    // host stacks, or base frames (host or device): the chunked pipeline of the blocking calls, enqueue only, with
+    // this rank's slot of the gather buffer as its (device) destination
+    uint8_t* d_rec = nullptr;
+    bool rec_on_host = false;
+    st = pipeline_enqueue(c, src, nframes_local, d, cap, mine, &d_rec, &rec_on_host);
+  } else {
+    st = enqueue_extract(c, d_stacks, frame_stride, nframes_local, d, cap, mine);
+  }
   // a ragged shard leaves trailing slots unused: their headers read "no keypoints" (n = n_total = 0, level starts 0)
   if (st == PISLAM_OK && nframes_local < slots_per_rank) {
     cudaError_t e = cudaMemset2DAsync(mine + rec_bytes * (size_t)nframes_local, rec_bytes, 0, REC_HEADER_WORDS * 4,
@@ -1832,6 +1844,20 @@ int pislam_b200_extract_allgather(pislam_ctx* c, const uint8_t* d_stacks, size_t
   g.ptr = d_all_records;
   CK(cudaEventRecord(g.done, c->comm_stream));
   return st;
+}
+}  // namespace
+
+int pislam_b200_extract_allgather(pislam_ctx* c, const uint8_t* stacks, size_t frame_stride, int nframes_local,
+                                  int slots_per_rank, const pislam_pyramid_desc* d, int cap, void* d_all_records) {
+  const FrameSource src = {stacks, false, 0, frame_stride, 0};
+  return extract_allgather_impl(c, src, nframes_local, slots_per_rank, d, cap, d_all_records);
+}
+
+int pislam_b200_extract_frames_allgather(pislam_ctx* c, const uint8_t* frames, int frame_pitch, size_t frame_stride,
+                                         int nframes_local, int blur, int slots_per_rank, const pislam_pyramid_desc* d,
+                                         int cap, void* d_all_records) {
+  const FrameSource src = {frames, true, frame_pitch, frame_stride, blur};
+  return extract_allgather_impl(c, src, nframes_local, slots_per_rank, d, cap, d_all_records);
 }
 
 int pislam_b200_join(pislam_ctx* c) {

@@ -99,6 +99,26 @@ def worker(rank, world, port, frame_counts, out):
         ctx.synchronize()
         for b in range(3):
             check(bufs[b], "buffer %d after the 0,0,2,1,0 sequence" % b)
+        # (2b) HOST stacks and HOST base frames as the source of the rank's shard (chunked pipeline into the slot, then
+        # the same exchange), into a registered and into an unregistered buffer
+        if count:
+            from pislam_b200.pyramid import synthetic_base
+            bases = np.stack([synthetic_base(640, 480, 0x5EED0000 + 500 + f) for f in range(start, start + count)])
+        else:
+            bases = np.zeros((1, 480, 640), np.uint8)
+        for b in (1, 2):
+            bufs[b].fill_(0x33)
+        torch.cuda.synchronize()
+        dist.barrier()
+        st = ctx.extract_allgather_ptr(stacks.ctypes.data if count else 0, VGA.stack_bytes, count, desc, CAP,
+                                       bufs[1].data_ptr(), slots_per_rank=per)
+        st2 = ctx.extract_frames_allgather_ptr(bases.ctypes.data if count else 0, 640, 640 * 480, count, desc, CAP,
+                                               bufs[2].data_ptr(), slots_per_rank=per)
+        ctx.synchronize()
+        if st != 0 or st2 != 0:
+            failures.append("%d frames: host-source extract_allgather %d / frames_allgather %d" % (nframes, st, st2))
+        check(bufs[1], "host stacks -> registered buffer")
+        check(bufs[2], "host base frames -> unregistered buffer")
         # (3) extract_batch into this rank's slot, then the stand-alone in-place all-gather (even shards only:
         # pislam_b200_allgather moves whole slots and knows nothing about unused ones)
         if nframes == world * per:
