@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "pislam/Fast.h"
+#include "pislam/Harris.h"
 #include "pislam/Orb.h"
 #include "pislam/Util.h"
 
@@ -78,6 +79,19 @@ int main(int argc, char** argv) {
   printf("stages: %zu features, keypoints %016llx, descriptors %016llx, %.2f ms (first pass %.2f ms)\n", points.size(),
          (unsigned long long)fnv1a(points.data(), points.size() * 4),
          (unsigned long long)fnv1a(descriptors.data(), descriptors.size() * 4), ms, ms_first);
+
+  // pislam::harrisScoreSobel point by point: a keypoint's score byte IS its Harris code (255 = unscored overrun flag)
+  {
+    int checked = 0, same = 0;
+    for (size_t i = 0; i < points.size() && checked < 16; i += points.size() / 16 + 1) {
+      const uint32_t p = points[i];
+      if (pislam::decodeFastScore(p) == 255) continue;
+      ++checked;
+      same += pislam::harrisScoreSobel<IMG_W>(img, (int)pislam::decodeFastX(p), (int)pislam::decodeFastY(p), 1 << 15) ==
+              pislam::decodeFastScore(p);
+    }
+    printf("harrisScoreSobel: %d of %d sampled keypoint scores reproduced\n", same, checked);
+  }
 
   // the same frame through the fused whole-pyramid call
   pislam_pyramid_desc d;

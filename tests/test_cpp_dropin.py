@@ -22,8 +22,10 @@ def test_demo_loop_on_fixture(fixture_stack):
         out = subprocess.run([os.path.join(ROOT, "examples", "demo"), raw], stdout=subprocess.PIPE, text=True,
                              check=True, timeout=120).stdout
     lines = out.strip().splitlines()
-    assert len(lines) == 2, out
-    for ln in lines:
+    assert len(lines) == 3, out
+    m = re.search(r"harrisScoreSobel: (\d+) of (\d+)", lines[1])
+    assert m and m.group(1) == m.group(2) and int(m.group(2)) >= 8, lines[1]
+    for ln in (lines[0], lines[2]):
         m = re.search(r"(\d+) features, keypoints ([0-9a-f]{16}), descriptors ([0-9a-f]{16})", ln)
         assert m, ln
         assert (m.group(1), m.group(2), m.group(3)) == ("1754", "1ab0b92100c9c317", "af0ceaba8d844310"), ln
