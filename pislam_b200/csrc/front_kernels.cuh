@@ -89,6 +89,7 @@ struct FrontParams {
   int log_bucket, bucket_limit;
   int cap;      // record capacity per frame; also the size of the staging overflow region
   int npieces;  // per frame
+  const uint8_t* zeros;  // >= 16 KB of zeros, 16-byte aligned (PB_TMA_ZERO)
   int prefetch_dist;  // CTAs resident on the whole GPU (0: no L2 prefetch of a later CTA's tile)
   int tile_slot;   // staging entries every tile owns (a tile with more survivors reserves in the overflow region)
   int stage_cap;   // staging entries per frame = ntiles * tile_slot + cap
@@ -274,6 +275,13 @@ __device__ __noinline__ void test_candidate_inline(const uint8_t* s_pix, uint8_t
 #ifndef PB_TASK_LIST
 #define PB_TASK_LIST 1  // phase A compacts non-empty tasks before expanding their bits (0: expand per warp round)
 #endif
+#ifndef PB_WARP_SEG
+#define PB_WARP_SEG 0  // phases A/A2/B: per-warp list segments with register counters instead of shared atomics;
+                       // every warp expands the tasks it found itself (no block barrier between A and A2)
+#endif
+#ifndef PB_TMA_ZERO
+#define PB_TMA_ZERO 0  // the score tile is cleared by a TMA bulk copy from a zero page instead of a store loop
+#endif
 #ifndef PB_A2_ATOMIC
 #define PB_A2_ATOMIC 0  // phase A2: per-lane shared atomics instead of a warp scan + one elected atomic
 #endif
@@ -300,6 +308,7 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
   __shared__ uint32_t s_occ[NCELL / 32], s_bm[NCELL / 32];
   __shared__ uint32_t s_vmcol[A_COLS], s_vmrow[A_GROUPS + 1];  // phase-A validity masks per word column / row group
   __shared__ uint32_t s_nA, s_nB, s_nC, s_nS, s_nT;
+  __shared__ uint32_t s_nBw[NT / 32];  // PB_WARP_SEG: corners per warp segment of list B
   __shared__ uint32_t s_dense;  // a list overflowed: scores were written in place, phase D scans every cell
   __shared__ __align__(8) uint64_t s_bar;
   // the slot arrays reuse buffers that are dead by then: the pixels after phase C, the scores after phase D
@@ -325,7 +334,15 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
     if (tid == 0) {
       mbar_init(&s_bar, 1);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#if PB_TMA_ZERO
+      mbar_expect_tx(&s_bar, PIX_H * PIX_W + SC_H * SC_W);
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(s_score)),
+          "l"(P.zeros), "r"(SC_H * SC_W), "r"(smem_u32(&s_bar))
+          : "memory");
+#else
       mbar_expect_tx(&s_bar, PIX_H * PIX_W);
+#endif
       tma_load_3d(s_pix, &tmap, x0 - 8 - dxo, L.row_off + y0 - 4, frame, &s_bar);
 #if PB_L2_PREFETCH
       // CTAs are dispatched in linear order, so the CTA that takes over this CTA's slot is about one residency wave
@@ -395,7 +412,9 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
       }
     }
   } else {
-    for (int i = tid; i < SC_H * SC_W / 16; i += NT) reinterpret_cast<uint4*>(s_score)[i] = make_uint4(0u, 0u, 0u, 0u);
+    static_assert((SC_H * SC_W) % 16 == 0, "bulk copies move multiples of 16 bytes");
+    if (!(PB_TMA_ZERO && MODE == MODE_TMA))
+      for (int i = tid; i < SC_H * SC_W / 16; i += NT) reinterpret_cast<uint4*>(s_score)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (MODE == MODE_LDG) {
       // linear addressing like the reference's img[y][x] on a uint8_t(*)[vstep]: a column past the pitch is the
       // start of the next row (the overrun blocks of Fast.h:36-40,61 read there when w is close to vstep);
@@ -428,6 +447,14 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
     const uint32_t nT_s = smem_u32(&s_nT);
     uint2* const s_task = reinterpret_cast<uint2*>(s_listB);  // list B is dead until phase B
 #endif
+#if PB_WARP_SEG
+    // every warp lists its non-empty tasks in its own quarter of the task list (at most 4 per lane = 128 per warp)
+    // with a register counter, then expands them itself: no shared atomic, no block barrier between A and A2
+    constexpr int SEG_T = ((A_TASKS + NT - 1) / NT) * 32;  // tasks a warp can own: 128 (64-row tiles) / 64
+    uint2* const my_task = s_task + (tid >> 5) * SEG_T;
+    uint32_t cntT = 0;
+    static_assert((NT / 32) * SEG_T * 8 <= CAP_B * 2, "per-warp task segments fit list B");
+#endif
     for (int task = tid; task < ((A_TASKS + 31) & ~31); task += NT) {
       // tasks A_TASKS.. of the last warp fall below the score tile (no valid row): they only take part in the scan
       const int g = task / A_COLS, wx = task - g * A_COLS;
@@ -443,15 +470,30 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
       // (one ballot per warp round), then expand their bits into list A with dense lanes (phase A2)
       const uint32_t nz = __ballot_sync(0xffffffffu, acc != 0u);
       if (nz == 0u) continue;
+#if PB_WARP_SEG
+      if (acc) my_task[cntT + __popc(nz & ((1u << lane) - 1u))] = make_uint2(acc, (uint32_t)((r0 << 8) | (4 * wx)));
+      cntT += (uint32_t)__popc(nz);
+    }
+    __syncwarp();
+#else
       const uint32_t tpos = warp_atom_shared_add(nT_s, (uint32_t)__popc(nz)) + __popc(nz & ((1u << lane) - 1u));
       if (acc) s_task[tpos] = make_uint2(acc, (uint32_t)((r0 << 8) | (4 * wx)));
     }
     __syncthreads();
+#endif
 #if defined(PB_EXPERIMENT_STOP) && PB_EXPERIMENT_STOP == 2
     return;
 #endif
 
     // ---- phase A2: candidate bits of the non-empty tasks -> list A -----------------------------------
+#if PB_WARP_SEG
+    const int nT = (int)cntT;  // this warp's tasks
+    for (int base = 0; base < nT; base += 32) {
+      const int ti = base + lane;
+      const uint2 te = ti < nT ? my_task[ti] : make_uint2(0u, 0u);
+      uint32_t acc = te.x;
+      const int idx0 = (int)te.y;
+#else
     const int nT = (int)s_nT;  // <= 256 tasks
     for (int base = 0; base < nT; base += NT) {
       if (base + (tid & ~31) >= nT) break;  // whole warps without a task
@@ -459,6 +501,7 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
       const uint2 te = ti < nT ? s_task[ti] : make_uint2(0u, 0u);
       uint32_t acc = te.x;
       const int idx0 = (int)te.y;
+#endif
 #else
       if (__ballot_sync(0xffffffffu, acc != 0u) == 0u) continue;  // a warp without candidates (30 %) skips the rest
       const int idx0 = (r0 << 8) | (4 * wx);
@@ -517,6 +560,12 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
 
     // ---- phase B: exact FAST-9 on the candidates (Fast.h:54-158) ---------------------------------
     const int nA = min((int)s_nA, CAP_A);
+#if PB_WARP_SEG
+    // corners go to the warp's own quarter of list B, counted in a register (no shared atomic per round)
+    constexpr int SEG_B = CAP_B / (NT / 32);
+    uint16_t* const my_listB = s_listB + (tid >> 5) * SEG_B;
+    uint32_t cntB = 0;
+#endif
     for (int base = 0; base < nA; base += NT) {
       const int i = base + tid;
       const uint32_t rc = i < nA ? s_listA[i] : 0u;
@@ -524,26 +573,49 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
       const bool corner = i < nA && fast9_packed_at(s_pix + (ry + 3) * PIX_W + dxo + 4 + sx, PIX_W, t);
       // columns >= w-border are never scored (Fast.h:172): they keep the raw 0xff flag
       const bool scored = (x0 - 4 + sx) < xs_end;
+#if PB_WARP_SEG
+      const uint32_t bal = __ballot_sync(0xffffffffu, corner);
+      const uint32_t pos = cntB + __popc(bal & ((1u << lane) - 1u));
+      cntB += (uint32_t)__popc(bal);
+      if (corner) {
+        if (pos < (uint32_t)SEG_B) {
+          my_listB[pos] = (uint16_t)(rc | (scored ? 0u : 0x8000u));
+#else
       const uint32_t pos = warp_reserve(corner, &s_nB);
       if (corner) {
         if (pos < CAP_B) {
           s_listB[pos] = (uint16_t)(rc | (scored ? 0u : 0x8000u));
+#endif
         } else {  // list B is full: score in place
           score_corner_inline(s_pix, s_score, rc, dxo, scored, P.harris_t);
           s_dense = 1u;
         }
       }
     }
+#if PB_WARP_SEG
+    if (lane == 0) s_nBw[tid >> 5] = min(cntB, (uint32_t)SEG_B);
+#endif
     __syncthreads();
 #if defined(PB_EXPERIMENT_STOP) && PB_EXPERIMENT_STOP == 4
     return;
 #endif
 
     // ---- phase C: Harris code of every flagged pixel (Fast.h:166-180, Harris.h:80-248) ------------
+#if PB_WARP_SEG
+    const int nB0 = (int)s_nBw[0], nB1 = nB0 + (int)s_nBw[1], nB2 = nB1 + (int)s_nBw[2], nB = nB2 + (int)s_nBw[3];
+    static_assert(NT / 32 == 4, "four list-B segments");
+#else
     const int nB = min((int)s_nB, CAP_B);
+#endif
     for (int base = 0; base < nB; base += NT) {
       const int i = base + tid;
+#if PB_WARP_SEG
+      // corner i of the concatenated segments
+      const int si = i < nB0 ? i : (i < nB1 ? SEG_B + i - nB0 : (i < nB2 ? 2 * SEG_B + i - nB1 : 3 * SEG_B + i - nB2));
+      const uint32_t e = i < nB ? s_listB[si] : 0u;
+#else
       const uint32_t e = i < nB ? s_listB[i] : 0u;
+#endif
       const uint32_t rc = e & 0x7fffu;
       const int ry = rc_row(rc), sx = rc_col(rc);
       uint32_t code = 0;

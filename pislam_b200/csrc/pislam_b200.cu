@@ -180,6 +180,7 @@ struct pislam_ctx {
   EncodeTiledFn encode = nullptr;
   uint32_t* d_brief = nullptr;    // pattern offsets for the 36-byte patch pitch
   uint32_t* d_brief48 = nullptr;  // ... for the 48-byte pitch of the TMA patch buffers
+  uint8_t* d_zeros = nullptr;     // 16 KB of zeros: source of the score tile's bulk clear (front_tile_kernel, PB_TMA_ZERO)
   // literal stages
   DevBuf img, out, kp, desc, aux0, aux1;
   // fused path
@@ -436,6 +437,7 @@ void fill_front_params(const pislam_ctx* c, FrontParams& P, const uint8_t* src, 
   P.bucket_limit = g.d.bucket_limit;
   P.cap = g.cap;
   P.npieces = g.npieces;
+  P.zeros = c->d_zeros;
   P.prefetch_dist = c->front_resident_ctas;
   P.tile_slot = kTileSlot;
   P.stage_cap = g.ntiles * kTileSlot + g.cap;
@@ -965,6 +967,8 @@ int pislam_b200_create(pislam_ctx** out, int device, size_t max_stack_bytes, int
       const uint32_t o1 = (uint32_t)((t[4 * i + 3] + 15) * OT_W + (t[4 * i + 2] + 15));
       offs[i] = o0 | (o1 << 16);
     }
+    if ((e = cudaMalloc(&c->d_zeros, 16384)) != cudaSuccess) { st = -(int)e; break; }
+    if ((e = cudaMemset(c->d_zeros, 0, 16384)) != cudaSuccess) { st = -(int)e; break; }
     if ((e = cudaMalloc(&c->d_brief48, offs.size() * 4)) != cudaSuccess) { st = -(int)e; break; }
     if ((e = cudaMemcpy(c->d_brief48, offs.data(), offs.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
       st = -(int)e;
@@ -1008,6 +1012,7 @@ int pislam_b200_destroy(pislam_ctx* c) {
   if (c->d_brief) cudaFree(c->d_brief);
   if (c->h_rec) cudaFreeHost(c->h_rec);
   if (c->d_brief48) cudaFree(c->d_brief48);
+  if (c->d_zeros) cudaFree(c->d_zeros);
   for (int i = 0; i < pislam_ctx::kMaxChunks; ++i) {
     if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
     if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
@@ -1767,16 +1772,11 @@ int extract_allgather_impl(pislam_ctx* c, const FrameSource& src, int nframes_lo
   // a gather that is still filling this buffer must finish before the kernels write into it again; with two
   // alternating buffers the previous gather (other buffer) keeps running under this batch's kernels
   pislam_ctx::GatherSlot& g = c->gathers[c->gather_turn];
-  bool known = false;
   for (int i = 0; i < pislam_ctx::kGatherSlots; ++i)
-    if (c->gathers[i].ptr == d_all_records) {
-      CK(cudaStreamWaitEvent(c->stream, c->gathers[i].done, 0));
-      known = true;
-    }
+    if (c->gathers[i].ptr == d_all_records) CK(cudaStreamWaitEvent(c->stream, c->gathers[i].done, 0));
   // a buffer beyond the tracked ones evicts the oldest entry: from then on nothing remembers that entry's gather, so
   // order this call (and through the stream everything later) behind it
   if (g.ptr && g.ptr != d_all_records) CK(cudaStreamWaitEvent(c->stream, g.done, 0));
-  (void)known;
   P2pPeers peers;
   memset(&peers, 0, sizeof(peers));
   uint32_t epoch = 0;
