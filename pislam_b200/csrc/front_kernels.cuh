@@ -30,7 +30,7 @@ constexpr int SC_W = TW + 8;        // score tile: origin (x0-4, y0-1)
 constexpr int SC_WW = SC_W / 4;     // score-tile words per row
 constexpr int CELLS_X = TW / 2;
 constexpr int A_COLS = SC_WW;       // phase A: 34 word columns
-constexpr int A_ROWS = 5;           // phase A: rows per thread
+constexpr int A_ROWS = 6;           // phase A: rows per task (the 66 score rows of a 64-row tile are 11 groups of 6)
 
 // Everything that depends on the tile height.  Two heights are compiled: 64 for batches (per-tile set-up, the
 // one-warp tail phases and the halo rows are amortised over twice the pixels: 0.310 vs 0.347 ms per 256 VGA
@@ -74,7 +74,7 @@ struct LevelInfo {
                       // for its flags to land on column border-1 of the NEXT row, which fastExtract reads
 };
 
-struct TileDesc {
+struct __align__(16) TileDesc {  // one 16-byte load per CTA
   int level, x0, y0, piece0;  // piece of segment s = piece0 + s*ntile_cols
 };
 
@@ -89,7 +89,7 @@ struct FrontParams {
   int log_bucket, bucket_limit;
   int cap;      // record capacity per frame; also the size of the staging overflow region
   int npieces;  // per frame
-  const uint8_t* zeros;  // >= 16 KB of zeros, 16-byte aligned (PB_TMA_ZERO)
+  const uint8_t* zeros;  // >= 16 KB of zeros, 16-byte aligned: source of the score tile's bulk clear (MODE_TMA)
   int prefetch_dist;  // CTAs resident on the whole GPU (0: no L2 prefetch of a later CTA's tile)
   int tile_slot;   // staging entries every tile owns (a tile with more survivors reserves in the overflow region)
   int stage_cap;   // staging entries per frame = ntiles * tile_slot + cap
@@ -146,14 +146,6 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
 // --------------------------------------------------------------------------------------------------
 // SWAR helpers: four pixels per 32-bit word
 // --------------------------------------------------------------------------------------------------
-// bit 7 of every byte: (byte of d) > t, for a uniform t in 0..255; k7 = (0x7f - (t & 0x7f)) * 0x01010101.
-// With s = low 7 bits + k7 (bit 7 of s: low7 > t7): t < 128 needs d | s, t >= 128 needs d & s; `m_or` is
-// all-ones / zero accordingly, so both cases are one three-input logic op.
-__device__ __forceinline__ uint32_t bytes_gt(uint32_t d, uint32_t k7, uint32_t m_or) {
-  const uint32_t s = (d & 0x7f7f7f7fu) + k7;
-  return (d & s) | ((d | s) & m_or);
-}
-
 // One lane of the (fully converged) warp adds `v` to the shared counter at `addr`; every lane gets the old value.
 // elect.sync keeps ptxas from wrapping the atomic into its generic warp-aggregation sequence (17 instructions
 // per call site, 3.6 % of the kernel's instructions before), REDUX broadcasts the result.
@@ -182,43 +174,6 @@ __device__ __forceinline__ uint32_t warp_reserve(bool want, uint32_t* counter) {
 __device__ __forceinline__ void warp_push(bool want, uint16_t item, uint16_t* list, uint32_t* counter) {
   const uint32_t pos = warp_reserve(want, counter);
   if (want) list[pos] = item;
-}
-
-// Superset form of bytes_gt for t < 128, K = (0x7f - t) * 0x01010101: bit 7 of d | (d + K).  Bytes >= 128 pass
-// through d itself; for bytes < 128 the byte sum d + (127 - t) + carry-in stays below 256, so bit 7 says
-// d + carry-in > t.  A carry from the byte below (that byte is >= 129 + t) can only turn a tie d == t into a
-// pass, never a pass into a fail: fine for a pre-test whose survivors are tested exactly (1 extra candidate in
-// 200 000 on the synthetic set), and it saves the per-byte masking.
-__device__ __forceinline__ uint32_t bytes_gt_loose(uint32_t d, uint32_t K) { return d | (d + K); }
-
-// Phase-A arithmetic for one word column `c` (row pitch PIX_W/4 words): rows 0..10 of the column and the words
-// left/right of rows 3..7.  Bit 8k+i of the result: pixel k of row i+3 passes (N or S) and (E or W).
-template <bool T_LT_128>
-__device__ __forceinline__ uint32_t pretest_rows(const uint32_t* c, int t) {
-  constexpr int PW = (TW + 32) / 4, R = 5;
-  const uint32_t K = (0x7fu - (uint32_t)(t & 0x7f)) * 0x01010101u;
-  uint32_t I[R + 6];
-#pragma unroll
-  for (int q = 0; q < R + 6; ++q) I[q] = c[q * PW];
-  uint32_t V[R + 3];
-#pragma unroll
-  for (int q = 0; q < R + 3; ++q) {
-    const uint32_t d = __vabsdiffu4(I[q + 3], I[q]);
-    V[q] = T_LT_128 ? bytes_gt_loose(d, K) : bytes_gt(d, K, 0u);
-  }
-  uint32_t acc = 0;
-#pragma unroll
-  for (int i = 0; i < R; ++i) {
-    const uint32_t C = I[i + 3];
-    const uint32_t* cr = c + (i + 3) * PW;
-    const uint32_t dE = __vabsdiffu4(__funnelshift_r(C, cr[1], 24), C);   // pixels x+3 .. x+6 against x .. x+3
-    const uint32_t dW = __vabsdiffu4(__funnelshift_r(cr[-1], C, 8), C);   // pixels x-3 .. x
-    const uint32_t ew = T_LT_128 ? (bytes_gt_loose(dE, K) | bytes_gt_loose(dW, K))
-                                 : (bytes_gt(dE, K, 0u) | bytes_gt(dW, K, 0u));
-    const uint32_t m = (V[i] | V[i + 3]) & ew;
-    acc |= (m >> (7 - i)) & (0x01010101u << i);
-  }
-  return acc;
 }
 
 // if (bits & bit) { *(uint16_t*)addr = v; addr += 2; }  as two predicated instructions
@@ -250,7 +205,7 @@ __device__ __forceinline__ bool nms_survives(const uint8_t* q, int pitch) {
 // Work lists keep every phase dense: A (SWAR pre-test, all pixels) -> candidates -> B (exact FAST-9)
 // -> corners -> C (Harris code) -> non-zero scores -> D (non-max) -> survivors -> D2 (bucket top-k)
 // -> bitmap over output slots -> E (rank by popcount prefix = the reference's order).
-static_assert(A_ROWS == 5, "pretest_rows and the 5-bit row mask are written for 5 rows per task");
+static_assert(A_ROWS >= 5 && A_ROWS <= 8, "one flag bit per row and pixel inside a 32-bit task mask");
 
 // Slow path of a corner that did not fit into list B: score it in place (rarely executed, kept out of line)
 // List entries are "rc" codes: (score-tile row << 8) | score-tile column (rows <= 65, columns <= 135), so that
@@ -272,28 +227,7 @@ __device__ __noinline__ void test_candidate_inline(const uint8_t* s_pix, uint8_t
     score_corner_inline(s_pix, s_score, rc, dxo, scored, harris_t);
 }
 
-#ifndef PB_TASK_LIST
-#define PB_TASK_LIST 1  // phase A compacts non-empty tasks before expanding their bits (0: expand per warp round)
-#endif
-#ifndef PB_WARP_SEG
-#define PB_WARP_SEG 0  // phases A/A2/B: per-warp list segments with register counters instead of shared atomics;
-                       // every warp expands the tasks it found itself (no block barrier between A and A2)
-#endif
-#ifndef PB_TMA_ZERO
-#define PB_TMA_ZERO 0  // the score tile is cleared by a TMA bulk copy from a zero page instead of a store loop
-#endif
-#ifndef PB_A2_ATOMIC
-#define PB_A2_ATOMIC 0  // phase A2: per-lane shared atomics instead of a warp scan + one elected atomic
-#endif
-#ifndef PB_L2_PREFETCH
-#define PB_L2_PREFETCH 0  // every CTA prefetches into L2 the tile a CTA one residency wave later will stage
-#endif
-#ifndef PB_WARP_TAIL
-#define PB_WARP_TAIL 1  // phases D/D2/E of a tile with <= 32 non-zero scores run in warp 0 alone
-#endif
-#ifndef PB_TAIL_MAX
-#define PB_TAIL_MAX 32  // non-zero scores up to which one warp runs the tail
-#endif
+constexpr unsigned TAIL_MAX = 32;  // non-zero scores up to which one warp runs phases D/D2/E alone (64 / 128: no gain)
 template <int MODE, int TH_>
 __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(const __grid_constant__ FrontParams P,
                                                                               const __grid_constant__ CUtensorMap tmap) {
@@ -307,8 +241,8 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
                                                      // phase-A task list before that
   __shared__ uint32_t s_occ[NCELL / 32], s_bm[NCELL / 32];
   __shared__ uint32_t s_vmcol[A_COLS], s_vmrow[A_GROUPS + 1];  // phase-A validity masks per word column / row group
-  __shared__ uint32_t s_nA, s_nB, s_nC, s_nS, s_nT;
-  __shared__ uint32_t s_nBw[NT / 32];  // PB_WARP_SEG: corners per warp segment of list B
+  __shared__ uint32_t s_nA, s_nC, s_nS;
+  __shared__ uint32_t s_nW[NT / 32];  // entries per warp segment: of the task list (A1 -> A2), then of list B (B -> C)
   __shared__ uint32_t s_dense;  // a list overflowed: scores were written in place, phase D scans every cell
   __shared__ __align__(8) uint64_t s_bar;
   // the slot arrays reuse buffers that are dead by then: the pixels after phase C, the scores after phase D
@@ -334,39 +268,18 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
     if (tid == 0) {
       mbar_init(&s_bar, 1);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#if PB_TMA_ZERO
       mbar_expect_tx(&s_bar, PIX_H * PIX_W + SC_H * SC_W);
       asm volatile(
           "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(s_score)),
           "l"(P.zeros), "r"(SC_H * SC_W), "r"(smem_u32(&s_bar))
           : "memory");
-#else
-      mbar_expect_tx(&s_bar, PIX_H * PIX_W);
-#endif
       tma_load_3d(s_pix, &tmap, x0 - 8 - dxo, L.row_off + y0 - 4, frame, &s_bar);
-#if PB_L2_PREFETCH
-      // CTAs are dispatched in linear order, so the CTA that takes over this CTA's slot is about one residency wave
-      // further on: fetch its tile into L2 now, and its own box load will not wait for DRAM
-      if (P.prefetch_dist > 0) {
-        const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x + (unsigned)P.prefetch_dist;
-        const unsigned fy = lin / gridDim.x, fx = lin - fy * gridDim.x;
-        if (fy < gridDim.y) {
-          const TileDesc nd = P.tiles[fx];
-          const int ndxo = (nd.x0 - 8) & 15;
-          asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(&tmap),
-                       "r"(nd.x0 - 8 - ndxo), "r"(P.lv[nd.level].row_off + nd.y0 - 4), "r"((int)fy)
-                       : "memory");
-        }
-      }
-#endif
     }
   }
   if (tid == 0) {
     s_nA = 0;
-    s_nB = 0;
     s_nC = 0;
     s_nS = 0;
-    s_nT = 0;
     s_dense = 0;
   }
   if (tid < NCELL / 32) {
@@ -377,7 +290,7 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
     const int wx = tid - NCELL / 32;
     const int x = x0 - 4 + 4 * wx;
     const int nlo = min(max(max(B, x0 - 1) - x, 0), 4), nhi = min(max(min(L.xend, x0 + TW + 1) - x, 0), 4);
-    s_vmcol[wx] = nlo < nhi ? ((0x01010101u << (8 * nlo)) & (0x01010101u >> (8 * (4 - nhi)))) * 0x1fu : 0u;
+    s_vmcol[wx] = nlo < nhi ? ((0x01010101u << (8 * nlo)) & (0x01010101u >> (8 * (4 - nhi)))) * ((1u << A_ROWS) - 1u) : 0u;
   } else if (MODE != MODE_SCOREMAP && tid < NCELL / 32 + A_COLS + A_GROUPS + 1) {
     // ... and rows of row group g (B <= y < h-B, inside the score tile)
     const int g = tid - (NCELL / 32 + A_COLS);
@@ -413,7 +326,7 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
     }
   } else {
     static_assert((SC_H * SC_W) % 16 == 0, "bulk copies move multiples of 16 bytes");
-    if (!(PB_TMA_ZERO && MODE == MODE_TMA))
+    if (MODE != MODE_TMA)  // (the TMA mode clears the score tile with a bulk copy from a zero page, issued above)
       for (int i = tid; i < SC_H * SC_W / 16; i += NT) reinterpret_cast<uint4*>(s_score)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (MODE == MODE_LDG) {
       // linear addressing like the reference's img[y][x] on a uint8_t(*)[vstep]: a column past the pitch is the
@@ -432,93 +345,72 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
     }
     __syncthreads();
     if (MODE == MODE_TMA) mbar_wait(&s_bar, 0);
-#if defined(PB_EXPERIMENT_STOP) && PB_EXPERIMENT_STOP == 1
-    return;
-#endif
 
-    // ---- phase A: SWAR pre-test on the four compass ring pixels ---------------------------------
-    // A 9-arc always contains two neighbouring compass points (ring 1,5,9,13), so a corner needs
-    // |p-c| > t on (N or S) and on (E or W).  One thread owns a word column (4 pixels) and 5 rows:
-    // |I[q+3]-I[q]| > t serves as the S test of row q and the N test of row q+3.  The test only has to be
-    // a superset of the corners (phase B is exact), which buys the carry-tolerant compare of bytes_gt_loose.
+    // ---- phase A: SWAR pre-tests, a cascade over (word column, 6-row group) tasks --------------------
+    // A 9-arc always contains two neighbouring compass points (ring 1,5,9,13) and two neighbouring diagonal points
+    // (ring 3,7,11,15), so a corner needs |p-c| > t on (N or S), (E or W), (NE or SW) and (SE or NW).  The tests
+    // only have to be supersets of the corners (phase B is exact), which buys the carry-tolerant compare of
+    // bytes_gt_loose.  |I[q+3]-I[q]| > t serves as the S test of row q and the N test of row q+3.
     const int t = P.fast_t & 0xff;  // Fast.h:58 keeps the low byte
     const uint32_t listA_s = smem_u32(s_listA), nA_s = smem_u32(&s_nA);
-#if PB_TASK_LIST
-    const uint32_t nT_s = smem_u32(&s_nT);
-    uint2* const s_task = reinterpret_cast<uint2*>(s_listB);  // list B is dead until phase B
-#endif
-#if PB_WARP_SEG
-    // every warp lists its non-empty tasks in its own quarter of the task list (at most 4 per lane = 128 per warp)
-    // with a register counter, then expands them itself: no shared atomic, no block barrier between A and A2
-    constexpr int SEG_T = ((A_TASKS + NT - 1) / NT) * 32;  // tasks a warp can own: 128 (64-row tiles) / 64
-    uint2* const my_task = s_task + (tid >> 5) * SEG_T;
+    // ---- phase A1: which tasks have a pixel passing (N or S) at all?  (all pixels; one in four does) ----
+    // Lane = word column, so no task decode and conflict-free loads; warp w takes row groups w, w+4, ...; the
+    // two word columns beyond the 32 lanes are one extra round of the last warp.  Non-empty tasks go to the
+    // warp's own segment of the task list (register counter, no atomic).
+    constexpr int NWARP = NT / 32, SEG_T = 256, XCOLS = A_COLS - 32;
+    constexpr int MAIN_ROUNDS = (A_GROUPS + NWARP - 1) / NWARP;  // of warp 0
+    static_assert(XCOLS == 2 && XCOLS * A_GROUPS <= 32, "the columns beyond the 32 lanes fit one warp round");
+    static_assert((MAIN_ROUNDS + 1) * 32 <= SEG_T && NWARP * SEG_T <= CAP_B, "task segments fit list B");
+    static_assert(NWARP == 4, "four task segments");
+    const int wp = tid >> 5;
+    const uint32_t* const pixw = reinterpret_cast<const uint32_t*>(s_pix) + (dxo >> 2) + 1;
+    uint16_t* const my_task = s_listB + wp * SEG_T;  // list B is dead until phase B
     uint32_t cntT = 0;
-    static_assert((NT / 32) * SEG_T * 8 <= CAP_B * 2, "per-warp task segments fit list B");
-#endif
-    for (int task = tid; task < ((A_TASKS + 31) & ~31); task += NT) {
-      // tasks A_TASKS.. of the last warp fall below the score tile (no valid row): they only take part in the scan
-      const int g = task / A_COLS, wx = task - g * A_COLS;
-      const int r0 = g * A_ROWS;
-      const uint32_t vm = s_vmcol[wx] & s_vmrow[g];  // bit 8k+i: the flag of pixel k, row r0+i matters here
-      uint32_t acc = 0;                              // bit 8k+i: that pixel is a candidate
-      if (vm) {
-        const uint32_t* c = reinterpret_cast<const uint32_t*>(s_pix) + r0 * (PIX_W / 4) + (dxo >> 2) + 1 + wx;
-        acc = (t < 128 ? pretest_rows<true>(c, t) : pretest_rows<false>(c, t)) & vm;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    {
+      // one (row group, word column) task per lane: emits its code when a pixel of the task passes (N or S)
+      auto probe = [&](bool have, int g, int wx, uint32_t vmc) {
+        bool any = false;
+        if (have && (vmc & s_vmrow[g]) != 0u) {
+          const uint32_t* c = pixw + g * (A_ROWS * (PIX_W / 4)) + wx;
+          any = t < 128 ? ns_any<true, PIX_W / 4, A_ROWS>(c, t) : ns_any<false, PIX_W / 4, A_ROWS>(c, t);
+        }
+        const uint32_t nz = __ballot_sync(0xffffffffu, any);
+        if (any) my_task[cntT + __popc(nz & lt_mask)] = (uint16_t)((g << 8) | wx);
+        cntT += (uint32_t)__popc(nz);
+      };
+      const uint32_t vmc = s_vmcol[lane];
+#pragma unroll 1
+      for (int g = wp; g < A_GROUPS; g += NWARP) probe(true, g, lane, vmc);
+      if (wp == NWARP - 1) {
+        const bool have = lane < XCOLS * A_GROUPS;
+        const int wx = 32 + (lane & 1);
+        probe(have, lane >> 1, wx, have ? s_vmcol[wx] : 0u);
       }
-#if PB_TASK_LIST
-      // only one task in eight has a candidate at all (but then ~8 of them): first compact the non-empty tasks
-      // (one ballot per warp round), then expand their bits into list A with dense lanes (phase A2)
-      const uint32_t nz = __ballot_sync(0xffffffffu, acc != 0u);
-      if (nz == 0u) continue;
-#if PB_WARP_SEG
-      if (acc) my_task[cntT + __popc(nz & ((1u << lane) - 1u))] = make_uint2(acc, (uint32_t)((r0 << 8) | (4 * wx)));
-      cntT += (uint32_t)__popc(nz);
     }
-    __syncwarp();
-#else
-      const uint32_t tpos = warp_atom_shared_add(nT_s, (uint32_t)__popc(nz)) + __popc(nz & ((1u << lane) - 1u));
-      if (acc) s_task[tpos] = make_uint2(acc, (uint32_t)((r0 << 8) | (4 * wx)));
-    }
+    if (lane == 0) s_nW[wp] = cntT;
     __syncthreads();
-#endif
-#if defined(PB_EXPERIMENT_STOP) && PB_EXPERIMENT_STOP == 2
-    return;
-#endif
-
-    // ---- phase A2: candidate bits of the non-empty tasks -> list A -----------------------------------
-#if PB_WARP_SEG
-    const int nT = (int)cntT;  // this warp's tasks
-    for (int base = 0; base < nT; base += 32) {
-      const int ti = base + lane;
-      const uint2 te = ti < nT ? my_task[ti] : make_uint2(0u, 0u);
-      uint32_t acc = te.x;
-      const int idx0 = (int)te.y;
-#else
-    const int nT = (int)s_nT;  // <= 256 tasks
+    const int nT0 = (int)s_nW[0], nT1 = nT0 + (int)s_nW[1], nT2 = nT1 + (int)s_nW[2], nT = nT2 + (int)s_nW[3];
     for (int base = 0; base < nT; base += NT) {
       if (base + (tid & ~31) >= nT) break;  // whole warps without a task
       const int ti = base + tid;
-      const uint2 te = ti < nT ? s_task[ti] : make_uint2(0u, 0u);
-      uint32_t acc = te.x;
-      const int idx0 = (int)te.y;
-#endif
-#else
-      if (__ballot_sync(0xffffffffu, acc != 0u) == 0u) continue;  // a warp without candidates (30 %) skips the rest
-      const int idx0 = (r0 << 8) | (4 * wx);
-#endif
+      const int si = ti < nT0 ? ti : (ti < nT1 ? SEG_T + ti - nT0 : (ti < nT2 ? 2 * SEG_T + ti - nT1 : 3 * SEG_T + ti - nT2));
+      // ---- phase A2: compass and diagonal tests of the surviving tasks, one per lane of the concatenated
+      // segments (dense lanes; 4 % of the pixels come out as candidates, 2.6 per corner) -> list A
+      uint32_t acc = 0;  // bit 8k+i: pixel k of row r0+i is a candidate
+      int idx0 = 0;
+      if (ti < nT) {
+        const uint32_t code = s_listB[si];
+        const int g = (int)(code >> 8), wx = (int)(code & 0xffu);
+        const uint32_t* c = pixw + g * (A_ROWS * (PIX_W / 4)) + wx;
+        const uint32_t vm = s_vmcol[wx] & s_vmrow[g];  // bit 8k+i: the flag of pixel k, row r0+i matters here
+        if (t < 128)
+          acc = pretest_rows<true, PIX_W / 4, A_ROWS>(c, t) & diag_rows<true, PIX_W / 4, A_ROWS>(c, t) & vm;
+        else
+          acc = pretest_rows<false, PIX_W / 4, A_ROWS>(c, t) & diag_rows<false, PIX_W / 4, A_ROWS>(c, t) & vm;
+        idx0 = ((g * A_ROWS) << 8) | (4 * wx);
+      }
       const uint32_t cnt = (uint32_t)__popc(acc);
-#if PB_A2_ATOMIC
-      // every lane reserves its own run: the order of list A is irrelevant (phase B treats candidates alike), and
-      // 32 same-address shared atomics are cheaper than a five-step shuffle scan plus one elected atomic
-      uint32_t pos = 0;
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "setp.ne.u32 p, %2, 0;\n\t"
-          "@p atom.shared.add.u32 %0, [%1], %2;\n\t}"
-          : "+r"(pos)
-          : "r"(nA_s), "r"(cnt)
-          : "memory");
-#else
       // one list reservation per warp for all rows
       constexpr uint32_t amask = 0xffffffffu;
       uint32_t incl = cnt;
@@ -529,9 +421,8 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
       }
       const uint32_t pos0 = warp_atom_shared_add(nA_s, __shfl_sync(0xffffffffu, incl, 31));
       uint32_t pos = pos0 + incl - cnt;
-#endif
       if (pos + cnt <= CAP_A) {
-        // 20 predicated stores (a loop over the set bits runs with ~3 of 32 lanes busy); explicit shared
+        // 24 predicated stores (a loop over the set bits runs with ~3 of 32 lanes busy); explicit shared
         // addresses: the compiler otherwise rebuilds the shared window base inside every predicated block
         uint32_t a = listA_s + 2u * pos;
 #pragma unroll
@@ -554,68 +445,43 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
       }
     }
     __syncthreads();
-#if defined(PB_EXPERIMENT_STOP) && PB_EXPERIMENT_STOP == 3
-    return;
-#endif
 
     // ---- phase B: exact FAST-9 on the candidates (Fast.h:54-158) ---------------------------------
     const int nA = min((int)s_nA, CAP_A);
-#if PB_WARP_SEG
     // corners go to the warp's own quarter of list B, counted in a register (no shared atomic per round)
     constexpr int SEG_B = CAP_B / (NT / 32);
     uint16_t* const my_listB = s_listB + (tid >> 5) * SEG_B;
     uint32_t cntB = 0;
-#endif
     for (int base = 0; base < nA; base += NT) {
       const int i = base + tid;
       const uint32_t rc = i < nA ? s_listA[i] : 0u;
       const int ry = rc_row(rc), sx = rc_col(rc);
-      const bool corner = i < nA && fast9_packed_at(s_pix + (ry + 3) * PIX_W + dxo + 4 + sx, PIX_W, t);
+      const bool corner = i < nA && fast9_prmt_at(s_pix + (ry + 3) * PIX_W + dxo + 4 + sx, PIX_W, t);
       // columns >= w-border are never scored (Fast.h:172): they keep the raw 0xff flag
       const bool scored = (x0 - 4 + sx) < xs_end;
-#if PB_WARP_SEG
       const uint32_t bal = __ballot_sync(0xffffffffu, corner);
       const uint32_t pos = cntB + __popc(bal & ((1u << lane) - 1u));
       cntB += (uint32_t)__popc(bal);
       if (corner) {
         if (pos < (uint32_t)SEG_B) {
           my_listB[pos] = (uint16_t)(rc | (scored ? 0u : 0x8000u));
-#else
-      const uint32_t pos = warp_reserve(corner, &s_nB);
-      if (corner) {
-        if (pos < CAP_B) {
-          s_listB[pos] = (uint16_t)(rc | (scored ? 0u : 0x8000u));
-#endif
         } else {  // list B is full: score in place
           score_corner_inline(s_pix, s_score, rc, dxo, scored, P.harris_t);
           s_dense = 1u;
         }
       }
     }
-#if PB_WARP_SEG
-    if (lane == 0) s_nBw[tid >> 5] = min(cntB, (uint32_t)SEG_B);
-#endif
+    if (lane == 0) s_nW[tid >> 5] = min(cntB, (uint32_t)SEG_B);
     __syncthreads();
-#if defined(PB_EXPERIMENT_STOP) && PB_EXPERIMENT_STOP == 4
-    return;
-#endif
 
     // ---- phase C: Harris code of every flagged pixel (Fast.h:166-180, Harris.h:80-248) ------------
-#if PB_WARP_SEG
-    const int nB0 = (int)s_nBw[0], nB1 = nB0 + (int)s_nBw[1], nB2 = nB1 + (int)s_nBw[2], nB = nB2 + (int)s_nBw[3];
+    const int nB0 = (int)s_nW[0], nB1 = nB0 + (int)s_nW[1], nB2 = nB1 + (int)s_nW[2], nB = nB2 + (int)s_nW[3];
     static_assert(NT / 32 == 4, "four list-B segments");
-#else
-    const int nB = min((int)s_nB, CAP_B);
-#endif
     for (int base = 0; base < nB; base += NT) {
       const int i = base + tid;
-#if PB_WARP_SEG
       // corner i of the concatenated segments
       const int si = i < nB0 ? i : (i < nB1 ? SEG_B + i - nB0 : (i < nB2 ? 2 * SEG_B + i - nB1 : 3 * SEG_B + i - nB2));
       const uint32_t e = i < nB ? s_listB[si] : 0u;
-#else
-      const uint32_t e = i < nB ? s_listB[i] : 0u;
-#endif
       const uint32_t rc = e & 0x7fffu;
       const int ry = rc_row(rc), sx = rc_col(rc);
       uint32_t code = 0;
@@ -660,18 +526,10 @@ __global__ void __launch_bounds__(NT, TileCfg<TH_>::MIN_CTAS) front_tile_kernel(
     atomicOr((lb == 0 ? s_bm : s_occ) + (slot >> 5), 1u << (slot & 31));
     return slot;
   };
-#if defined(PB_EXPERIMENT_STOP)
-  return;  // timing experiment only (results are garbage): PB_EXPERIMENT_STOP = 1 after staging, 2 after phase A,
-           // 3 after A2, 4 after B, 5 after C (no tail)
-#endif
-#if PB_WARP_TAIL
   // A typical tile has a few dozen non-zero scores and keeps a handful of keypoints: one warp finishes it with
   // warp-level synchronisation instead of three more block barriers; the other warps retire.
-  const bool warp_tail = !s_dense && s_nC <= (unsigned)PB_TAIL_MAX;
+  const bool warp_tail = !s_dense && s_nC <= TAIL_MAX;
   if (warp_tail && tid >= 32) return;
-#else
-  const bool warp_tail = false;
-#endif
   const int tail_nt = warp_tail ? 32 : NT;  // threads that take part in phases D and D2
   auto tail_sync = [&]() {
     if (warp_tail) __syncwarp();

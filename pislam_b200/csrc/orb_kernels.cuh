@@ -67,26 +67,13 @@ __device__ __forceinline__ void build_disc_tables(uint32_t* s_wx, uint32_t* s_w1
   }
 }
 
-// q[0..11] hold the 48 bytes of this lane's patch row starting at its 16-byte chunk; column x-15 is byte `ob`.
-// Produces w[0..7] (byte j = column x-15+j) and this warp's moments.  Lane 31 contributes nothing.
-__device__ __forceinline__ void moments_from_chunks(uint32_t q[13], uint32_t ob, const uint32_t* s_wx,
-                                                    const uint32_t* s_w1, uint32_t w[8], int32_t& m10, int32_t& m01) {
+// Moments of the warp's patch from the aligned row words w[0..7] (byte j of the row = column x-15+j): lane r owns
+// row r-15, lane 31 contributes nothing.
+__device__ __forceinline__ void moments_from_rows(const uint32_t w[8], const uint32_t* s_wx, const uint32_t* s_w1,
+                                                  int32_t& m10, int32_t& m01) {
   const int lane = threadIdx.x & 31;
   m10 = 0;
   m01 = 0;
-  q[12] = 0u;
-  // drop (ob >> 2) leading words, then shift by the remaining (ob & 3) bytes
-  if (ob & 8) {
-#pragma unroll
-    for (int k = 0; k < 11; ++k) q[k] = q[k + 2];
-  }
-  if (ob & 4) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) q[k] = q[k + 1];
-  }
-  const uint32_t sh = (ob & 3) * 8;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) w[k] = __funnelshift_r(q[k], q[k + 1], sh);
   if (lane < 31) {
     const int dy = lane - 15;
     const int ady = dy < 0 ? -dy : dy;
@@ -100,6 +87,26 @@ __device__ __forceinline__ void moments_from_chunks(uint32_t q[13], uint32_t ob,
   }
   m10 = __reduce_add_sync(0xffffffffu, m10);
   m01 = __reduce_add_sync(0xffffffffu, m01);
+}
+
+// q[0..11] hold the 48 bytes of this lane's patch row starting at its 16-byte chunk; column x-15 is byte `ob`
+// (any value per lane).  Produces w[0..7] (byte j = column x-15+j) and this warp's moments.
+__device__ __forceinline__ void moments_from_chunks(uint32_t q[13], uint32_t ob, const uint32_t* s_wx,
+                                                    const uint32_t* s_w1, uint32_t w[8], int32_t& m10, int32_t& m01) {
+  q[12] = 0u;
+  // drop (ob >> 2) leading words, then shift by the remaining (ob & 3) bytes
+  if (ob & 8) {
+#pragma unroll
+    for (int k = 0; k < 11; ++k) q[k] = q[k + 2];
+  }
+  if (ob & 4) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) q[k] = q[k + 1];
+  }
+  const uint32_t sh = (ob & 3) * 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) w[k] = __funnelshift_r(q[k], q[k + 1], sh);
+  moments_from_rows(w, s_wx, s_w1, m10, m01);
 }
 
 // Loads patch row (lane-15) of the keypoint at (x, y) from global memory (linear addressing, bounded by `end`)

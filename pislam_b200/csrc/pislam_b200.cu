@@ -180,7 +180,7 @@ struct pislam_ctx {
   EncodeTiledFn encode = nullptr;
   uint32_t* d_brief = nullptr;    // pattern offsets for the 36-byte patch pitch
   uint32_t* d_brief48 = nullptr;  // ... for the 48-byte pitch of the TMA patch buffers
-  uint8_t* d_zeros = nullptr;     // 16 KB of zeros: source of the score tile's bulk clear (front_tile_kernel, PB_TMA_ZERO)
+  uint8_t* d_zeros = nullptr;     // 16 KB of zeros: source of the score tile's bulk clear (front_tile_kernel, MODE_TMA)
   // literal stages
   DevBuf img, out, kp, desc, aux0, aux1;
   // fused path

@@ -78,11 +78,16 @@ def main():
     np.save(fp, frames)
     print("frames built in %.1f s" % (time.time() - t0), flush=True)
     ref = None
+    rec_bytes = None
     for rnd in range(2):
         for lib in libs:
             out = "/tmp/ab_rec_%s.npy" % os.path.basename(lib)
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", lib, fp, out],
-                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", lib, fp, out],
+                                   stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+            except subprocess.TimeoutExpired:
+                print("%s TIMED OUT" % lib, flush=True)
+                continue
             sys.stdout.write(r.stdout)
             if r.returncode != 0:
                 print("%s FAILED (%d): %s" % (lib, r.returncode, r.stderr[-600:]), flush=True)
@@ -92,8 +97,32 @@ def main():
                 if ref is None:
                     ref = rec
                 else:
-                    print("    records identical to %s: %s" % (os.path.basename(libs[0]), bool((rec == ref).all())),
-                          flush=True)
+                    same = bool((rec == ref).all())
+                    print("    records identical to %s: %s" % (os.path.basename(libs[0]), same), flush=True)
+                    if not same:
+                        describe_difference(ref, rec)
+
+
+def describe_difference(ref, rec):
+    """Which part of the records differs (counts, keypoints, descriptors, levels) and in how many frames."""
+    from pislam_b200 import api
+    lay = api.record_layout(CAP, WORDS)
+    a, b = ref.reshape(F, lay["bytes"]), rec.reshape(F, lay["bytes"])
+    n_a, n_b = a[:, :4].copy().view(np.uint32)[:, 0], b[:, :4].copy().view(np.uint32)[:, 0]
+    parts = {"header": (0, lay["kp"]), "keypoints": (lay["kp"], lay["desc"]),
+             "descriptors": (lay["desc"], lay["level"]), "levels": (lay["level"], lay["bytes"])}
+    for name, (lo, hi) in parts.items():
+        bad = int((a[:, lo:hi] != b[:, lo:hi]).any(axis=1).sum())
+        print("      %-12s differs in %d of %d frames" % (name, bad, F), flush=True)
+    print("      keypoints per frame: reference %.2f, this build %.2f; frames with another count: %d"
+          % (n_a.mean(), n_b.mean(), int((n_a != n_b).sum())), flush=True)
+    f = int(np.argmax((a != b).any(axis=1)))
+    ka = a[f, lay["kp"]:lay["kp"] + 4 * int(n_a[f])].copy().view(np.uint32)
+    kb = b[f, lay["kp"]:lay["kp"] + 4 * int(n_b[f])].copy().view(np.uint32)
+    only_a, only_b = np.setdiff1d(ka, kb), np.setdiff1d(kb, ka)
+    fmt = lambda v: ["(s%d x%d y%d)" % (e >> 24, (e >> 12) & 0xfff, e & 0xfff) for e in v[:6]]  # noqa: E731
+    print("      first differing frame %d: only in reference %s, only in this build %s"
+          % (f, fmt(only_a), fmt(only_b)), flush=True)
 
 
 if __name__ == "__main__":
