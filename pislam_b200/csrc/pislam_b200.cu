@@ -335,6 +335,8 @@ int pick_tile_height(const pislam_ctx* c, const pislam_pyramid_desc* d, int nfra
     const int iw = d->widths[l] - 2 * d->border, ih = d->heights[l] - 2 * d->border;
     if (iw > 0 && ih > 0) tiles64 += (long long)((iw + TW - 1) / TW) * ((ih + TH_BATCH - 1) / TH_BATCH);
   }
+  static const int forced = getenv("PISLAM_B200_TILE_H") ? atoi(getenv("PISLAM_B200_TILE_H")) : 0;  // timing experiments
+  if (forced == TH_SMALL || forced == TH_BATCH) return forced;
   return tiles64 * nframes < 4LL * c->num_sms ? TH_SMALL : TH_BATCH;
 }
 

@@ -22,6 +22,11 @@ F, STEPS, CAP, WORDS = 256, 30, 2048, 8
 
 
 def child(lib, frames_path, out_path):
+    lib, _, envs = lib.partition("@")  # "ab/lib_x.so@VAR=VALUE,VAR2=VALUE2": environment of this variant
+    for kv in filter(None, envs.split(",")):
+        k, _, v = kv.partition("=")
+        os.environ[k] = v
+    tag = os.path.basename(lib) + ("@" + envs if envs else "")
     os.environ["PISLAM_B200_LIB"] = os.path.abspath(lib)
     import torch
     from pislam_b200 import api, pyramid
@@ -59,8 +64,8 @@ def child(lib, frames_path, out_path):
     rec = d_rec.cpu().numpy()
     np.save(out_path, rec)
     hdr = rec.reshape(F, rec_bytes)[:, :8].copy().view(np.uint32)
-    print("%-22s front %.4f ms  order %.4f  orb %.4f  step %.4f ms  kpts/frame %.1f  records sha1 %s" % (
-        os.path.basename(lib), ms[0] / max(cnt[0], 1), ms[1] / max(cnt[1], 1), ms[2] / max(cnt[2], 1),
+    print("%-30s front %.4f ms  order %.4f  orb %.4f  step %.4f ms  kpts/frame %.1f  records sha1 %s" % (
+        tag, ms[0] / max(cnt[0], 1), ms[1] / max(cnt[1], 1), ms[2] / max(cnt[2], 1),
         e0.elapsed_time(e1) / STEPS, hdr[:, 0].mean(), hashlib.sha1(rec.tobytes()).hexdigest()[:12]), flush=True)
     del d_stacks, d_rec, s
     ctx.close()
@@ -81,7 +86,7 @@ def main():
     rec_bytes = None
     for rnd in range(2):
         for lib in libs:
-            out = "/tmp/ab_rec_%s.npy" % os.path.basename(lib)
+            out = "/tmp/ab_rec_%s.npy" % os.path.basename(lib).replace("@", "_").replace("=", "_").replace(",", "_")
             try:
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", lib, fp, out],
                                    stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
