@@ -43,8 +43,8 @@ struct TileCfg {
   static constexpr int SC_H = TH + 2;         // score-tile rows
   static constexpr int CELLS_Y = TH / 2;
   static constexpr int NCELL = CELLS_X * CELLS_Y;  // 2048 / 1024 2x2 cells per tile
-  static constexpr int A_GROUPS = (SC_H + A_ROWS - 1) / A_ROWS;  // 14 / 7 row groups
-  static constexpr int A_TASKS = A_COLS * A_GROUPS;              // 476 / 238 (word column, row group) tasks
+  static constexpr int A_GROUPS = (SC_H + A_ROWS - 1) / A_ROWS;  // 11 / 6 row groups
+  static constexpr int A_TASKS = A_COLS * A_GROUPS;              // 374 / 204 (word column, row group) tasks
   // rows the last (partly invalid) row group of phase A reads beyond the staged tile: kept inside s_pix by padding
   static constexpr int PIX_PAD_ROWS = A_GROUPS * A_ROWS + 6 > PIX_H ? A_GROUPS * A_ROWS + 6 - PIX_H : 0;
   // Work-list capacities.  Natural images need ~130 candidates / ~50 corners per 4096 pixels; the lists are sized
@@ -57,7 +57,6 @@ struct TileCfg {
   static constexpr int MIN_CTAS = TH == 64 ? 7 : 10;
   static_assert(NCELL % 1024 == 0 && NCELL / 32 <= 64, "phase E: one or two bitmap words per lane of one warp");
   static_assert(CAP_A >= CAP_B && CAP_B >= NCELL, "list A: one entry per corner of list B; list B: one survivor per cell");
-  static_assert(CAP_B * 2 >= ((A_TASKS + 31) & ~31) * 8, "list B hosts the phase-A task list (8 bytes per task)");
   static_assert(NCELL / 32 + A_COLS + A_GROUPS + 1 <= NT, "set-up roles fit the CTA");
 };
 constexpr int TH_BATCH = 64, TH_SMALL = 32;
@@ -202,9 +201,10 @@ __device__ __forceinline__ bool nms_survives(const uint8_t* q, int pitch) {
 // --------------------------------------------------------------------------------------------------
 // The fused tile kernel
 // --------------------------------------------------------------------------------------------------
-// Work lists keep every phase dense: A (SWAR pre-test, all pixels) -> candidates -> B (exact FAST-9)
-// -> corners -> C (Harris code) -> non-zero scores -> D (non-max) -> survivors -> D2 (bucket top-k)
-// -> bitmap over output slots -> E (rank by popcount prefix = the reference's order).
+// Work lists keep every phase dense: A1 ((N or S) on every task of 6 rows x 4 pixels) -> surviving tasks -> A2
+// (compass + diagonal SWAR tests) -> candidates -> B (exact FAST-9) -> corners -> C (Harris code) -> non-zero
+// scores -> D (non-max) -> survivors -> D2 (bucket top-k) -> bitmap over output slots -> E (rank by popcount
+// prefix = the reference's order).
 static_assert(A_ROWS >= 5 && A_ROWS <= 8, "one flag bit per row and pixel inside a 32-bit task mask");
 
 // Slow path of a corner that did not fit into list B: score it in place (rarely executed, kept out of line)
