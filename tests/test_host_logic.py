@@ -52,3 +52,32 @@ def test_compass_pretest_never_rejects_a_corner(oracle):
             corners[16:h - 16, 16:w - 16] = out[16:h - 16, 16:w - 16] != 0
             assert corners.sum() > 0
             assert not (corners & ~pre).any()
+
+
+def test_diagonal_pretest_never_rejects_a_corner_and_removes_a_third_of_the_candidates(oracle):
+    """Phase A2 of the tile kernel adds (NE or SW) and (SE or NW) on the ring pixels (+-2, +-2) to the compass test:
+    a 9-arc contains two neighbouring diagonal ring pixels as well.  Necessary for every FAST-9 corner of the oracle,
+    and on synthetic frames it removes more than a third of the compass test's candidates (2.6
+    candidates per corner against 4.6 over the 8-level bench pyramids)."""
+    lay = pyramid_layout(640, 480, nlevels=3)
+    n0 = n1 = nc = 0
+    for stack, t in ((synthetic_stack(lay, 0), 20), (synthetic_stack(lay, 1), 20), (noise_stack(lay, 6), 40)):
+        for w, h, r in zip(lay.widths, lay.heights, lay.row_offsets):
+            img = np.ascontiguousarray(stack[r:r + h])
+            out = np.zeros_like(img)
+            oracle.fast_detect(img, out, 16, w, h, t)
+            I = img.astype(np.int32)
+            sh = lambda dx, dy: np.roll(np.roll(I, -dy, 0), -dx, 1)  # noqa: E731
+            u = {o: np.abs(sh(*o) - I) > t for o in ((0, -3), (3, 0), (0, 3), (-3, 0), (2, -2), (2, 2), (-2, 2), (-2, -2))}
+            compass = (u[(0, -3)] | u[(0, 3)]) & (u[(3, 0)] | u[(-3, 0)])
+            diag = (u[(2, -2)] | u[(-2, 2)]) & (u[(2, 2)] | u[(-2, -2)])
+            inner = np.zeros_like(compass)
+            inner[16:h - 16, 16:w - 16] = True
+            corners = inner & (out != 0)
+            assert not (corners & ~(compass & diag)).any()
+            if t == 20:  # the synthetic frames only: uniform noise passes everything
+                n0 += int((compass & inner).sum())
+                n1 += int((compass & diag & inner).sum())
+                nc += int(corners.sum())
+    assert nc > 2000
+    assert n1 < 0.65 * n0 and n1 < 4.0 * nc, (n0, n1, nc)
